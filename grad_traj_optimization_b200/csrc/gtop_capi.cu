@@ -1,0 +1,608 @@
+// gtop_capi.cu — implementation of the C ABI declared in include/gtop_c.h.
+// Host logic only: handle management, set-up packing, stream/copy orchestration; every compute
+// step is a launch of a kernel in eval_kernel.cu / sdf_kernels.cu.  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gtop_c.h"
+#include "gtop_types.cuh"
+#include "problem_setup.hpp"
+
+namespace gtop {
+cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
+                        const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
+                        int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
+                        int max_ctas, cudaStream_t stream);
+cudaError_t launch_fill(double* dist, uint8_t* occ, int64_t n, double dval, cudaStream_t st);
+cudaError_t launch_set_occupancy(const SdfView& S, uint8_t* occ, const double* pts_dev, int64_t n, cudaStream_t st);
+cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t* boxes_dev, int64_t n,
+                             cudaStream_t st);
+cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
+                       cudaStream_t st, cudaEvent_t* ev);
+cudaError_t launch_query(const SdfView& S, const double* pos_dev, int64_t n, double* dist_dev, double* grad_dev,
+                         unsigned long long* oob_dev, cudaStream_t st);
+}  // namespace gtop
+
+using namespace gtop;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(GTOP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+#define REQUIRE(cond, msg) \
+  do {                     \
+    if (!(cond)) return fail(GTOP_E_INVALID, msg); \
+  } while (0)
+
+struct gtop_sdf {
+  int device = 0;
+  SdfView view{};
+  double origin[3], map_size[3];
+  int64_t nvox = 0;
+  double* dist = nullptr;
+  uint8_t* occ = nullptr;
+  int32_t *d1 = nullptr, *d2 = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float last_ms[4] = {0, 0, 0, 0};
+};
+
+struct gtop_problems {
+  int device = 0;
+  int np = 0;
+  ProbLayout layout{};
+  gtop_params prm{};
+  std::vector<ProblemHost> host;
+  double* rec = nullptr;               // np * layout.stride doubles
+  unsigned long long* oob = nullptr;   // device counter
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  // staging for the *_host entry point (grown on demand)
+  double *dX = nullptr, *dcost = nullptr, *dgrad = nullptr;
+  int64_t cap = 0;
+};
+
+struct gtop_objective_ctx {
+  const gtop_sdf* sdf = nullptr;
+  const gtop_problems* problems = nullptr;
+  int problem = 0, step = 2, n = 0;
+  double *hx = nullptr, *hout = nullptr;  // pinned: x[n]; out = cost + grad[n]
+  double *dx = nullptr, *dout = nullptr;
+  cudaStream_t stream = nullptr;
+  int64_t evals = 0;
+};
+
+static EvalScalars make_scalars(const gtop_params& p, int step) {
+  EvalScalars E;
+  E.ws = (step == GTOP_OPT_FIRST_STEP) ? 0.0 : p.w_smooth;  // grad_traj_optimizer.cpp:412-415
+  E.wc = p.w_collision;
+  E.alpha = p.alpha;
+  E.d0 = p.d0;
+  E.inv_r = 1.0 / p.r;
+  E.alpha_over_r = p.alpha / p.r;
+  E.skip_collision = std::fabs(p.w_collision) < 1e-4 ? 1 : 0;  // :346
+  return E;
+}
+
+extern "C" {
+
+int gtop_abi_version(void) { return GTOP_ABI_VERSION; }
+const char* gtop_last_error(void) { return g_err.c_str(); }
+int64_t gtop_kernel_launch_count(void) { return g_launches.load(); }
+
+int gtop_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void gtop_params_default(gtop_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->time_limit_1 = 0.04, p->time_limit_2 = 0.06, p->deltat = 0.2;
+  p->w_smooth = 1.0, p->w_collision = 1.0;
+  p->alpha = 1.0, p->r = 1.0, p->d0 = 1.0;
+  p->alpha_v = 0.0, p->r_v = 1.0, p->v0 = 1.0;
+  p->alpha_a = 0.0, p->r_a = 1.0, p->a0 = 1.0;
+  p->bos = 3.0, p->vos = 8.0, p->aos = 10.0;
+  p->mean_v = 1.0, p->mean_a = 1.0, p->init_time = 0.0;
+  p->algorithm = 24, p->samples_per_segment = 30, p->vel_acc_penalty = 0;
+}
+
+int gtop_host_alloc(void** ptr, size_t bytes) {
+  REQUIRE(ptr, "null ptr");
+  CU(cudaMallocHost(ptr, bytes));
+  return GTOP_OK;
+}
+int gtop_host_free(void* ptr) {
+  if (ptr) CU(cudaFreeHost(ptr));
+  return GTOP_OK;
+}
+
+// ================================================================================ SDF map
+int gtop_sdf_create(const double origin[3], double resolution, const double map_size[3], int device, gtop_sdf** out) {
+  REQUIRE(origin && map_size && out, "null argument");
+  REQUIRE(resolution > 0.0, "resolution must be > 0");
+  REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  gtop_sdf* s = new gtop_sdf();
+  s->device = device;
+  int g[3];
+  for (int i = 0; i < 3; ++i) {
+    s->origin[i] = origin[i], s->map_size[i] = map_size[i];
+    g[i] = (int)std::ceil(map_size[i] / resolution);  // sdf_map.cpp:9
+    if (g[i] < 1 || g[i] > 16384) {
+      delete s;
+      return fail(GTOP_E_INVALID, "grid dimension out of range [1, 16384]");
+    }
+  }
+  SdfView& v = s->view;
+  v.nx = g[0], v.ny = g[1], v.nz = g[2];
+  v.ox = origin[0], v.oy = origin[1], v.oz = origin[2];
+  v.res = resolution, v.res_inv = 1 / resolution, v.half_res = 0.5 * resolution;
+  v.lox = origin[0] + 1e-4, v.loy = origin[1] + 1e-4, v.loz = origin[2] + 1e-4;  // sdf_map.cpp:56-57
+  v.hix = (origin[0] + map_size[0]) - 1e-4, v.hiy = (origin[1] + map_size[1]) - 1e-4,
+  v.hiz = (origin[2] + map_size[2]) - 1e-4;  // :62-63 with max_range = origin + map_size (:12)
+  s->nvox = (int64_t)g[0] * g[1] * g[2];
+  cudaError_t e = cudaMalloc(&s->dist, sizeof(double) * s->nvox);
+  if (e == cudaSuccess) e = cudaMalloc(&s->occ, s->nvox);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+  if (e != cudaSuccess) {
+    gtop_sdf_destroy(s);
+    return fail(GTOP_E_ALLOC, std::string("sdf allocation: ") + cudaGetErrorString(e));
+  }
+  v.dist = s->dist;
+  CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));  // sdf_map.cpp:22-23
+  ++g_launches;
+  CU(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return GTOP_OK;
+}
+
+int gtop_sdf_destroy(gtop_sdf* s) {
+  if (!s) return GTOP_OK;
+  cudaSetDevice(s->device);
+  cudaFree(s->dist), cudaFree(s->occ), cudaFree(s->d1), cudaFree(s->d2);
+  for (auto& e : s->ev)
+    if (e) cudaEventDestroy(e);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return GTOP_OK;
+}
+
+int gtop_sdf_grid(const gtop_sdf* s, int32_t grid[3]) {
+  REQUIRE(s && grid, "null argument");
+  grid[0] = s->view.nx, grid[1] = s->view.ny, grid[2] = s->view.nz;
+  return GTOP_OK;
+}
+
+int gtop_sdf_reset(gtop_sdf* s) {
+  REQUIRE(s, "null sdf");
+  CU(cudaSetDevice(s->device));
+  CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));
+  ++g_launches;
+  CU(cudaStreamSynchronize(s->stream));
+  return GTOP_OK;
+}
+
+int gtop_sdf_set_occupancy(gtop_sdf* s, const double* xyz, int64_t n) {
+  REQUIRE(s && (xyz || n == 0) && n >= 0, "bad argument");
+  if (n == 0) return GTOP_OK;
+  CU(cudaSetDevice(s->device));
+  double* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(double) * 3 * n));
+  cudaError_t e = cudaMemcpyAsync(d, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = launch_set_occupancy(s->view, s->occ, d, n, s->stream);
+  ++g_launches;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(d);
+  CU(e);
+  return GTOP_OK;
+}
+
+int gtop_sdf_set_occupancy_boxes(gtop_sdf* s, const int32_t* lo_hi, int64_t n) {
+  REQUIRE(s && (lo_hi || n == 0) && n >= 0, "bad argument");
+  if (n == 0) return GTOP_OK;
+  CU(cudaSetDevice(s->device));
+  int32_t* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(int32_t) * 6 * n));
+  cudaError_t e = cudaMemcpyAsync(d, lo_hi, sizeof(int32_t) * 6 * n, cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = launch_set_boxes(s->view.nx, s->view.ny, s->view.nz, s->occ, d, n, s->stream);
+  ++g_launches;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(d);
+  CU(e);
+  return GTOP_OK;
+}
+
+int gtop_sdf_update_esdf(gtop_sdf* s) {
+  REQUIRE(s, "null sdf");
+  CU(cudaSetDevice(s->device));
+  if (!s->d1) {
+    cudaError_t e = cudaMalloc(&s->d1, sizeof(int32_t) * s->nvox);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d2, sizeof(int32_t) * s->nvox);
+    if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("edt scratch: ") + cudaGetErrorString(e));
+  }
+  CU(launch_edt(s->occ, s->d1, s->d2, s->dist, s->view.nx, s->view.ny, s->view.nz, s->view.res, s->stream, s->ev));
+  g_launches += 3;
+  CU(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&s->last_ms[i], s->ev[i], s->ev[i + 1]);
+  cudaEventElapsedTime(&s->last_ms[3], s->ev[0], s->ev[3]);
+  return GTOP_OK;
+}
+
+int gtop_sdf_last_edt_ms(const gtop_sdf* s, float ms[4]) {
+  REQUIRE(s && ms, "null argument");
+  for (int i = 0; i < 4; ++i) ms[i] = s->last_ms[i];
+  return GTOP_OK;
+}
+
+int gtop_sdf_download_distance(const gtop_sdf* s, double* host) {
+  REQUIRE(s && host, "null argument");
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpy(host, s->dist, sizeof(double) * s->nvox, cudaMemcpyDeviceToHost));
+  return GTOP_OK;
+}
+int gtop_sdf_upload_distance(gtop_sdf* s, const double* host) {
+  REQUIRE(s && host, "null argument");
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpy(s->dist, host, sizeof(double) * s->nvox, cudaMemcpyHostToDevice));
+  return GTOP_OK;
+}
+int gtop_sdf_download_occupancy(const gtop_sdf* s, int32_t* host) {
+  REQUIRE(s && host, "null argument");
+  CU(cudaSetDevice(s->device));
+  std::vector<uint8_t> tmp(s->nvox);
+  CU(cudaMemcpy(tmp.data(), s->occ, s->nvox, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < s->nvox; ++i) host[i] = tmp[i];
+  return GTOP_OK;
+}
+int gtop_sdf_upload_occupancy(gtop_sdf* s, const int32_t* host) {
+  REQUIRE(s && host, "null argument");
+  CU(cudaSetDevice(s->device));
+  std::vector<uint8_t> tmp(s->nvox);
+  for (int64_t i = 0; i < s->nvox; ++i) tmp[i] = host[i] == 1 ? 1 : 0;
+  CU(cudaMemcpy(s->occ, tmp.data(), s->nvox, cudaMemcpyHostToDevice));
+  return GTOP_OK;
+}
+int gtop_sdf_distance_device_ptr(const gtop_sdf* s, const double** p) {
+  REQUIRE(s && p, "null argument");
+  *p = s->dist;
+  return GTOP_OK;
+}
+
+int gtop_sdf_query(const gtop_sdf* s, const double* pos, int64_t n, double* dist, double* grad, int64_t* n_oob) {
+  REQUIRE(s && n >= 0 && (n == 0 || (pos && dist && grad)), "bad argument");
+  if (n_oob) *n_oob = 0;
+  if (n == 0) return GTOP_OK;
+  CU(cudaSetDevice(s->device));
+  double *dp = nullptr, *dd = nullptr, *dg = nullptr;
+  unsigned long long* dc = nullptr;
+  cudaError_t e = cudaMalloc(&dp, sizeof(double) * 3 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dd, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dg, sizeof(double) * 3 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dc, sizeof(unsigned long long));
+  unsigned long long hc = 0;
+  if (e == cudaSuccess) e = cudaMemsetAsync(dc, 0, sizeof(unsigned long long), s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dp, pos, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = launch_query(s->view, dp, n, dd, dg, dc, s->stream);
+  ++g_launches;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dist, dd, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(grad, dg, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(dp), cudaFree(dd), cudaFree(dg), cudaFree(dc);
+  CU(e);
+  if (n_oob) *n_oob = (int64_t)hc;
+  return GTOP_OK;
+}
+
+// ================================================================================ problems
+static int finish_problems(gtop_problems* p, gtop_problems** out) {
+  const ProbLayout& L = p->layout;
+  std::vector<double> rec((size_t)p->np * L.stride);
+  for (int i = 0; i < p->np; ++i) pack_record(p->host[i], rec.data() + (size_t)i * L.stride);
+  cudaError_t e = cudaMalloc(&p->rec, sizeof(double) * rec.size());
+  if (e == cudaSuccess) e = cudaMemcpy(p->rec, rec.data(), sizeof(double) * rec.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&p->oob, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(p->oob, 0, sizeof(unsigned long long));
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    gtop_problems_destroy(p);
+    return fail(GTOP_E_ALLOC, std::string("problem upload: ") + cudaGetErrorString(e));
+  }
+  *out = p;
+  return GTOP_OK;
+}
+
+static int check_params(const gtop_params* prm) {
+  REQUIRE(prm, "null params");
+  REQUIRE(prm->samples_per_segment >= 1 && prm->samples_per_segment <= 4096, "samples_per_segment out of range");
+  REQUIRE(prm->r != 0.0, "r must be non-zero");
+  if (prm->vel_acc_penalty)
+    return fail(GTOP_E_INVALID, "vel_acc_penalty=1 (the block commented out upstream, :383-407) is not built yet");
+  return GTOP_OK;
+}
+
+int gtop_problems_create_dense(int32_t np, int32_t m, const double* seg_time, const double* L, const double* R,
+                               const double* Df, const gtop_params* prm, int device, gtop_problems** out) {
+  REQUIRE(np >= 1 && m >= 2 && seg_time && L && R && Df && out, "bad argument");
+  if (int rc = check_params(prm)) return rc;
+  REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  gtop_problems* p = new gtop_problems();
+  p->device = device, p->np = np, p->prm = *prm;
+  p->layout = make_layout(m, prm->samples_per_segment);
+  p->host.resize(np);
+  const size_t szL = (size_t)6 * m * (3 * m + 3), szR = (size_t)(3 * m + 3) * (3 * m + 3);
+  for (int i = 0; i < np; ++i) {
+    std::string err =
+        setup_from_dense(m, seg_time + (size_t)i * m, L + i * szL, R + i * szR, Df + (size_t)i * 18, *prm, p->host[i]);
+    if (!err.empty()) {
+      delete p;
+      return fail(GTOP_E_INVALID, "problem " + std::to_string(i) + ": " + err);
+    }
+  }
+  return finish_problems(p, out);
+}
+
+int gtop_problems_create_from_paths(int32_t np, int32_t m, const double* waypoints, const gtop_params* prm, int device,
+                                    gtop_problems** out) {
+  REQUIRE(np >= 1 && m >= 2 && waypoints && out, "bad argument");
+  if (int rc = check_params(prm)) return rc;
+  REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  gtop_problems* p = new gtop_problems();
+  p->device = device, p->np = np, p->prm = *prm;
+  p->layout = make_layout(m, prm->samples_per_segment);
+  p->host.resize(np);
+  // independent problems: set them up on all host threads
+  std::atomic<int> next(0), bad(-1);
+  std::vector<std::string> errs(np);
+  auto work = [&]() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= np) break;
+      errs[i] = setup_from_path(m, waypoints + (size_t)i * (m + 1) * 3, *prm, p->host[i]);
+      if (!errs[i].empty()) bad.store(i);
+    }
+  };
+  int nt = (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, np / 64));
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; ++i) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (bad.load() >= 0) {
+    const int i = bad.load();
+    std::string msg = "problem " + std::to_string(i) + ": " + errs[i];
+    delete p;
+    return fail(GTOP_E_INVALID, msg);
+  }
+  return finish_problems(p, out);
+}
+
+int gtop_problems_destroy(gtop_problems* p) {
+  if (!p) return GTOP_OK;
+  cudaSetDevice(p->device);
+  cudaFree(p->rec), cudaFree(p->oob), cudaFree(p->dX), cudaFree(p->dcost), cudaFree(p->dgrad);
+  for (auto& s : p->streams)
+    if (s) cudaStreamDestroy(s);
+  delete p;
+  return GTOP_OK;
+}
+
+int gtop_problems_dims(const gtop_problems* p, int32_t* np, int32_t* m, int32_t* n) {
+  REQUIRE(p, "null problems");
+  if (np) *np = p->np;
+  if (m) *m = p->layout.m;
+  if (n) *n = p->layout.n;
+  return GTOP_OK;
+}
+
+int gtop_problems_set_params(gtop_problems* p, const gtop_params* prm) {
+  REQUIRE(p, "null problems");
+  if (int rc = check_params(prm)) return rc;
+  REQUIRE(prm->samples_per_segment == p->prm.samples_per_segment, "samples_per_segment is fixed at creation");
+  p->prm = *prm;
+  return GTOP_OK;
+}
+
+int gtop_problems_seg_time(const gtop_problems* p, double* out) {
+  REQUIRE(p && out, "null argument");
+  for (int i = 0; i < p->np; ++i) std::memcpy(out + (size_t)i * p->layout.m, p->host[i].seg_time.data(), sizeof(double) * p->layout.m);
+  return GTOP_OK;
+}
+int gtop_problems_x0(const gtop_problems* p, double* out) {
+  REQUIRE(p && out, "null argument");
+  if (!p->host[0].has_path) return fail(GTOP_E_STATE, "x0 is only known for problems created from paths");
+  for (int i = 0; i < p->np; ++i) std::memcpy(out + (size_t)i * p->layout.n, p->host[i].x0.data(), sizeof(double) * p->layout.n);
+  return GTOP_OK;
+}
+int gtop_problems_bounds(const gtop_problems* p, double* lb, double* ub) {
+  REQUIRE(p && lb && ub, "null argument");
+  if (!p->host[0].has_path) return fail(GTOP_E_STATE, "bounds are only known for problems created from paths");
+  for (int i = 0; i < p->np; ++i) {
+    std::memcpy(lb + (size_t)i * p->layout.n, p->host[i].lb.data(), sizeof(double) * p->layout.n);
+    std::memcpy(ub + (size_t)i * p->layout.n, p->host[i].ub.data(), sizeof(double) * p->layout.n);
+  }
+  return GTOP_OK;
+}
+int gtop_problems_dense_L(const gtop_problems* p, int32_t i, double* L) {
+  REQUIRE(p && L && i >= 0 && i < p->np, "bad argument");
+  dense_L(p->host[i], L);
+  return GTOP_OK;
+}
+int gtop_problems_dense_R(const gtop_problems* p, int32_t i, double* R) {
+  REQUIRE(p && R && i >= 0 && i < p->np, "bad argument");
+  dense_R(p->host[i], R);
+  return GTOP_OK;
+}
+int gtop_problems_Df(const gtop_problems* p, int32_t i, double* Df) {
+  REQUIRE(p && Df && i >= 0 && i < p->np, "bad argument");
+  for (int a = 0; a < 3; ++a)
+    for (int j = 0; j < 6; ++j) Df[j * 3 + a] = p->host[i].Df[a * 6 + j];
+  return GTOP_OK;
+}
+
+int gtop_coeff_from_x(const gtop_problems* p, int32_t i, const double* x, double* coeff) {
+  REQUIRE(p && x && coeff && i >= 0 && i < p->np, "bad argument");
+  coeff_from_x(p->host[i], x, coeff);
+  return GTOP_OK;
+}
+
+// ================================================================================ evaluation
+static int check_eval(const gtop_sdf* sdf, const gtop_problems* pr, int64_t B, int64_t starts, int step) {
+  REQUIRE(sdf && pr, "null handle");
+  REQUIRE(sdf->device == pr->device, "sdf and problems live on different devices");
+  REQUIRE(B >= 0 && starts >= 1, "bad batch shape");
+  REQUIRE(step >= 0 && step <= 2, "step must be 0, 1 or 2");
+  return GTOP_OK;
+}
+
+int gtop_eval_batch_device(const gtop_sdf* sdf, const gtop_problems* pr, const double* X, int64_t B, int64_t off,
+                           int64_t starts, int step, double* cost, double* grad, void* stream) {
+  if (int rc = check_eval(sdf, pr, B, starts, step)) return rc;
+  if (B == 0) return GTOP_OK;
+  REQUIRE(X && cost && grad, "null device buffer");
+  CU(cudaSetDevice(pr->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : pr->streams[0];
+  CU(launch_eval(sdf->view, pr->layout, pr->rec, pr->np, make_scalars(pr->prm, step), X, B, off, starts, cost, grad,
+                 pr->oob, 0, st));
+  ++g_launches;
+  return GTOP_OK;
+}
+
+int gtop_eval_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, const double* X, int64_t B, int64_t off,
+                         int64_t starts, int step, double* cost, double* grad, int64_t* n_oob) {
+  if (int rc = check_eval(sdf, cpr, B, starts, step)) return rc;
+  if (n_oob) *n_oob = 0;
+  if (B == 0) return GTOP_OK;
+  REQUIRE(X && cost && grad, "null host buffer");
+  gtop_problems* pr = const_cast<gtop_problems*>(cpr);  // staging buffers are a cache
+  CU(cudaSetDevice(pr->device));
+  const int n = pr->layout.n;
+  if (pr->cap < B) {
+    cudaFree(pr->dX), cudaFree(pr->dcost), cudaFree(pr->dgrad);
+    pr->dX = pr->dcost = pr->dgrad = nullptr, pr->cap = 0;
+    cudaError_t e = cudaMalloc(&pr->dX, sizeof(double) * B * n);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->dgrad, sizeof(double) * B * n);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->dcost, sizeof(double) * B);
+    if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("eval staging: ") + cudaGetErrorString(e));
+    pr->cap = B;
+  }
+  const EvalScalars E = make_scalars(pr->prm, step);
+  // chunked 3-stream pipeline: H2D(x) | kernel | D2H(cost, grad) overlap across chunks
+  int64_t nchunk = std::min<int64_t>(12, (B + 2047) / 2048);
+  const int64_t per = (B + nchunk - 1) / nchunk;
+  for (int64_t c = 0; c < nchunk; ++c) {
+    const int64_t b0 = c * per, bn = std::min(per, B - b0);
+    if (bn <= 0) break;
+    cudaStream_t st = pr->streams[c % 3];
+    CU(cudaMemcpyAsync(pr->dX + b0 * n, X + b0 * n, sizeof(double) * bn * n, cudaMemcpyHostToDevice, st));
+    CU(launch_eval(sdf->view, pr->layout, pr->rec, pr->np, E, pr->dX + b0 * n, bn, off + b0, starts, pr->dcost + b0,
+                   pr->dgrad + b0 * n, pr->oob, 0, st));
+    ++g_launches;
+    CU(cudaMemcpyAsync(grad + b0 * n, pr->dgrad + b0 * n, sizeof(double) * bn * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cost + b0, pr->dcost + b0, sizeof(double) * bn, cudaMemcpyDeviceToHost, st));
+  }
+  for (auto& st : pr->streams) CU(cudaStreamSynchronize(st));
+  if (n_oob) return gtop_problems_take_out_of_map(pr, n_oob);
+  return GTOP_OK;
+}
+
+int gtop_problems_take_out_of_map(gtop_problems* p, int64_t* n) {
+  REQUIRE(p && n, "null argument");
+  CU(cudaSetDevice(p->device));
+  unsigned long long h = 0;
+  CU(cudaMemcpy(&h, p->oob, sizeof(h), cudaMemcpyDeviceToHost));
+  CU(cudaMemset(p->oob, 0, sizeof(h)));
+  *n = (int64_t)h;
+  return GTOP_OK;
+}
+
+// ================================================================================ NLopt callback
+int gtop_objective_ctx_create(const gtop_sdf* sdf, const gtop_problems* pr, int32_t problem, int step,
+                              gtop_objective_ctx** out) {
+  if (int rc = check_eval(sdf, pr, 1, 1, step)) return rc;
+  REQUIRE(out && problem >= 0 && problem < pr->np, "bad argument");
+  CU(cudaSetDevice(pr->device));
+  gtop_objective_ctx* c = new gtop_objective_ctx();
+  c->sdf = sdf, c->problems = pr, c->problem = problem, c->step = step, c->n = pr->layout.n;
+  cudaError_t e = cudaMallocHost(&c->hx, sizeof(double) * c->n);
+  if (e == cudaSuccess) e = cudaMallocHost(&c->hout, sizeof(double) * (c->n + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&c->dx, sizeof(double) * c->n);
+  if (e == cudaSuccess) e = cudaMalloc(&c->dout, sizeof(double) * (c->n + 1));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    gtop_objective_ctx_destroy(c);
+    return fail(GTOP_E_ALLOC, std::string("objective ctx: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return GTOP_OK;
+}
+
+int gtop_objective_ctx_set_step(gtop_objective_ctx* c, int step) {
+  REQUIRE(c && step >= 0 && step <= 2, "bad argument");
+  c->step = step;
+  return GTOP_OK;
+}
+
+int gtop_objective_ctx_destroy(gtop_objective_ctx* c) {
+  if (!c) return GTOP_OK;
+  cudaSetDevice(c->problems->device);
+  cudaFreeHost(c->hx), cudaFreeHost(c->hout), cudaFree(c->dx), cudaFree(c->dout);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return GTOP_OK;
+}
+
+int64_t gtop_objective_ctx_evals(const gtop_objective_ctx* c) { return c ? c->evals : 0; }
+
+double gtop_objective(unsigned n, const double* x, double* grad, void* vctx) {
+  gtop_objective_ctx* c = (gtop_objective_ctx*)vctx;
+  if (!c || !x || (int)n != c->n) {
+    g_err = "gtop_objective: bad context or dimension";
+    return HUGE_VAL;
+  }
+  const gtop_problems* pr = c->problems;
+  cudaError_t e = cudaSetDevice(pr->device);
+  std::memcpy(c->hx, x, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->dx, c->hx, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess)
+    e = launch_eval(c->sdf->view, pr->layout, pr->rec, pr->np, make_scalars(pr->prm, c->step), c->dx, 1, c->problem, 1,
+                    c->dout, c->dout + 1, pr->oob, 0, c->stream);
+  ++g_launches;
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(c->hout, c->dout, sizeof(double) * (n + 1), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    g_err = std::string("gtop_objective: ") + cudaGetErrorString(e);
+    return HUGE_VAL;
+  }
+  ++c->evals;
+  if (grad) std::memcpy(grad, c->hout + 1, sizeof(double) * n);
+  return c->hout[0];
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// sdf_kernels.cu — voxel-map kernels: occupancy scatter, exact Euclidean distance transform,
+// batched trilinear query.
+//
+// Replaces (reference paths relative to EpicOne1/grad_traj_optimization):
+//   SDFMap::resetBuffer       src/sdf_map.cpp:26-53
+//   SDFMap::setOccupancy      src/sdf_map.cpp:80-99   (isInMap :55-69, posToIndex :71-74)
+//   SDFMap::updateESDF3d      src/sdf_map.cpp:310-368 (fillESDF :266-308)
+//   SDFMap::getDistWithGradTrilinear   src/sdf_map.cpp:185-242  (k_query, test / utility path)
+//
+// EDT design.  The reference runs Felzenszwalb–Huttenlocher lower envelopes in fp64 along z, y, x.
+// The result is the exact unsigned EDT: d(v) = res * sqrt(min over occupied u of |v-u|^2) capped at
+// 10000, and 10000 everywhere for an empty map.  Here all three passes work on exact
+// int32 squared voxel distances, so the only floating-point step is the final res*sqrt(double(d2))
+// (IEEE-exact on both sides) and the output is bit-identical to the CPU path:
+//   pass z : warp per (x,y) column (z is the contiguous axis): ballot + clz/ffs give the nearest
+//            occupied voxel below and above each z in two coalesced sweeps.
+//   pass y : thread per (x,z) row, threads adjacent in z so every step's loads/stores coalesce;
+//            integer lower envelope (Meijster's formulation of the same parabola envelope) with the
+//            stack in per-thread local memory.
+//   pass x : same with thread per (y,z) row; fused epilogue min(res*sqrt(d2), old) -> fp64 buffer.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gtop_types.cuh"
+
+namespace gtop {
+
+static constexpr int kInf = 0x3fffffff;  // "no occupied voxel" marker for int32 squared distances
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fill(double* __restrict__ dist, uint8_t* __restrict__ occ, int64_t n, double dval) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    dist[i] = dval;
+    occ[i] = 0;
+  }
+}
+
+__global__ void k_set_occupancy(SdfView S, uint8_t* __restrict__ occ, const double* __restrict__ pts, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+  if (px < S.lox || py < S.loy || pz < S.loz || px > S.hix || py > S.hiy || pz > S.hiz) return;  // isInMap
+  const int ix = (int)floor(__dmul_rn(__dsub_rn(px, S.ox), S.res_inv));                         // posToIndex
+  const int iy = (int)floor(__dmul_rn(__dsub_rn(py, S.oy), S.res_inv));
+  const int iz = (int)floor(__dmul_rn(__dsub_rn(pz, S.oz), S.res_inv));
+  if (ix < 0 || iy < 0 || iz < 0 || ix >= S.nx || iy >= S.ny || iz >= S.nz) return;  // cannot happen in-map
+  occ[((int64_t)ix * S.ny + iy) * S.nz + iz] = 1;
+}
+
+__global__ void k_set_boxes(int nx, int ny, int nz, uint8_t* __restrict__ occ, const int32_t* __restrict__ boxes,
+                            int64_t nboxes) {
+  // one CTA per box; threads sweep the box with z fastest
+  for (int64_t bi = blockIdx.x; bi < nboxes; bi += gridDim.x) {
+    const int32_t* b = boxes + 6 * bi;
+    const int x0 = max(b[0], 0), y0 = max(b[1], 0), z0 = max(b[2], 0);
+    const int x1 = min(b[3], nx - 1), y1 = min(b[4], ny - 1), z1 = min(b[5], nz - 1);
+    if (x1 < x0 || y1 < y0 || z1 < z0) continue;
+    const int64_t dx = x1 - x0 + 1, dy = y1 - y0 + 1, dz = z1 - z0 + 1, tot = dx * dy * dz;
+    for (int64_t i = threadIdx.x; i < tot; i += blockDim.x) {
+      const int z = z0 + (int)(i % dz), y = y0 + (int)((i / dz) % dy), x = x0 + (int)(i / (dz * dy));
+      occ[((int64_t)x * ny + y) * nz + z] = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass z: warp per column.  out[z] = (z - nearest occupied z')^2, or kInf when the column is empty.
+__global__ void __launch_bounds__(256)
+k_edt_z(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t ncols, int nz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nchunk = (nz + 31) >> 5;
+  for (int64_t col = wid; col < ncols; col += nw) {
+    const uint8_t* __restrict__ o = occ + col * nz;
+    int32_t* __restrict__ d = out + col * nz;
+    // forward sweep: distance to the last occupied voxel at or below z
+    int last = -kInf;  // "none yet"
+    for (int c = 0; c < nchunk; ++c) {
+      const int z = (c << 5) + lane;
+      const bool oc = z < nz && o[z] != 0;
+      const unsigned mask = __ballot_sync(0xffffffffu, oc);
+      const unsigned below = mask & (0xffffffffu >> (31 - lane));
+      const int near = below ? ((c << 5) + 31 - __clz(below)) : last;
+      if (z < nz) d[z] = (near == -kInf) ? kInf : (z - near);
+      if (mask) last = (c << 5) + 31 - __clz(mask);
+    }
+    // backward sweep: nearest occupied at or above z, combine, square
+    int next = kInf;
+    for (int c = nchunk - 1; c >= 0; --c) {
+      const int z = (c << 5) + lane;
+      const bool oc = z < nz && o[z] != 0;
+      const unsigned mask = __ballot_sync(0xffffffffu, oc);
+      const unsigned above = mask & (0xffffffffu << lane);
+      const int near = above ? ((c << 5) + __ffs(above) - 1) : next;
+      if (z < nz) {
+        const int down = d[z];
+        const int up = (near == kInf) ? kInf : (near - z);
+        const int best = min(down, up);
+        d[z] = (best >= kInf) ? kInf : best * best;
+      }
+      if (mask) next = (c << 5) + __ffs(mask) - 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-D lower envelope of parabolas on one strided row, exact integer arithmetic.
+//   out[u] = min_i ( (u-i)^2 + g[i] ),   g[i] in [0, kInf]  (kInf = +inf)
+// Stack of (site, first index where the site wins) kept in local memory (16-bit entries: rows are
+// < 32768 long).  F(x,i) = (x-i)^2 + g(i).
+template <int MAXN, bool FINAL>
+__device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int64_t gstride, int n,
+                                             int32_t* __restrict__ out_i, double* __restrict__ out_d, double res) {
+  short s[MAXN];  // sites
+  short t[MAXN];  // t[q]: first x at which site s[q] is the minimiser
+  int gs[MAXN];   // g(s[q]) cached next to the stack (avoids a dependent strided re-load)
+  int q = -1;
+  for (int u = 0; u < n; ++u) {
+    const int gu = g[(int64_t)u * gstride];
+    if (gu >= kInf) continue;  // an infinite parabola never wins
+    // pop while the new parabola is below the top one at the top's start
+    while (q >= 0) {
+      const int x = t[q], dq = x - s[q], du = x - u;
+      if ((long long)dq * dq + gs[q] > (long long)du * du + gu) --q;
+      else break;
+    }
+    if (q < 0) {
+      q = 0, s[0] = (short)u, t[0] = 0, gs[0] = gu;
+    } else {
+      // Sep(i,u) = floor((u^2 - i^2 + g(u) - g(i)) / (2(u-i))): last x where site i still wins
+      const int i = s[q];
+      const long long num = (long long)u * u - (long long)i * i + (long long)gu - (long long)gs[q];
+      const int w = 1 + (int)(num / (2LL * (u - i)));
+      if (w < n) ++q, s[q] = (short)u, t[q] = (short)w, gs[q] = gu;
+    }
+  }
+  if (q < 0) {  // whole row infinite
+    for (int u = 0; u < n; ++u) {
+      if (FINAL) {
+        double* o = out_d + (int64_t)u * gstride;
+        *o = fmin(1.0e300, *o);  // res*sqrt(DBL_MAX) in the reference: never below the old value
+      } else {
+        out_i[(int64_t)u * gstride] = kInf;
+      }
+    }
+    return;
+  }
+  for (int u = n - 1; u >= 0; --u) {
+    while (q > 0 && t[q] > u) --q;
+    const int d = u - s[q];
+    const int val = d * d + gs[q];
+    if (FINAL) {
+      double* o = out_d + (int64_t)u * gstride;
+      *o = fmin(res * sqrt((double)val), *o);  // sdf_map.cpp:356-360
+    } else {
+      out_i[(int64_t)u * gstride] = val;
+    }
+  }
+}
+
+// pass y: row = (x,z); element y at ((x*ny + y)*nz + z)
+template <int MAXN>
+__global__ void __launch_bounds__(128)
+k_edt_y(const int32_t* __restrict__ in, int32_t* __restrict__ out, int nx, int ny, int nz) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (int64_t)nx * nz) return;
+  const int x = (int)(r / nz), z = (int)(r % nz);
+  const int64_t base = (int64_t)x * ny * nz + z;
+  envelope_row<MAXN, false>(in + base, nz, ny, out + base, nullptr, 0.0);
+}
+
+// pass x: row = (y,z); element x at (x*ny*nz + (y*nz + z)); writes the fp64 distance buffer
+template <int MAXN>
+__global__ void __launch_bounds__(128)
+k_edt_x(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, int ny, int nz, double res) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t plane = (int64_t)ny * nz;
+  if (r >= plane) return;
+  envelope_row<MAXN, true>(in + r, plane, nx, nullptr, dist + r, res);
+}
+
+template <int MAXN>
+static cudaError_t launch_yx(const int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
+                             cudaStream_t st, cudaEvent_t ev_mid) {
+  const int threads = 128;
+  {
+    const int64_t rows = (int64_t)nx * nz;
+    k_edt_y<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d1, d2, nx, ny, nz);
+  }
+  if (ev_mid) cudaEventRecord(ev_mid, st);
+  {
+    const int64_t rows = (int64_t)ny * nz;
+    k_edt_x<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d2, dist, nx, ny, nz, res);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill(double* dist, uint8_t* occ, int64_t n, double dval, cudaStream_t st) {
+  k_fill<<<148 * 8, 256, 0, st>>>(dist, occ, n, dval);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_occupancy(const SdfView& S, uint8_t* occ, const double* pts_dev, int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_set_occupancy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S, occ, pts_dev, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t* boxes_dev, int64_t n,
+                             cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)(n < 148 * 16 ? n : 148 * 16);
+  k_set_boxes<<<grid, 256, 0, st>>>(nx, ny, nz, occ, boxes_dev, n);
+  return cudaGetLastError();
+}
+
+// full EDT: occ -> d1 (z) -> d2 (y) -> dist (x).  ev[0..3] (nullable) bracket the three passes.
+cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
+                       cudaStream_t st, cudaEvent_t* ev) {
+  const int64_t ncols = (int64_t)nx * ny;
+  if (ev) cudaEventRecord(ev[0], st);
+  {
+    const int threads = 256;
+    int64_t blocks = (ncols * 32 + threads - 1) / threads;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    k_edt_z<<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
+  }
+  if (ev) cudaEventRecord(ev[1], st);
+  const int maxn = nx > ny ? nx : ny;
+  cudaError_t e;
+  if (maxn <= 256)
+    e = launch_yx<256>(d1, d2, dist, nx, ny, nz, res, st, ev ? ev[2] : nullptr);
+  else if (maxn <= 1024)
+    e = launch_yx<1024>(d1, d2, dist, nx, ny, nz, res, st, ev ? ev[2] : nullptr);
+  else if (maxn <= 4096)
+    e = launch_yx<4096>(d1, d2, dist, nx, ny, nz, res, st, ev ? ev[2] : nullptr);
+  else if (maxn <= 16384)
+    e = launch_yx<16384>(d1, d2, dist, nx, ny, nz, res, st, ev ? ev[2] : nullptr);
+  else
+    return cudaErrorInvalidValue;
+  if (ev) cudaEventRecord(ev[3], st);
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched getDistWithGradTrilinear (reference formula, :221-239); same rounding discipline as the
+// evaluation kernel for the index / diff arithmetic.
+__global__ void k_query(SdfView S, const double* __restrict__ pos, int64_t n, double* __restrict__ dist,
+                        double* __restrict__ grad, unsigned long long* __restrict__ oob) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
+  if (px < S.lox || py < S.loy || pz < S.loz || px > S.hix || py > S.hiy || pz > S.hiz) {
+    dist[i] = -1.0;
+    grad[3 * i] = grad[3 * i + 1] = grad[3 * i + 2] = 0.0;
+    atomicAdd(oob, 1ULL);
+    return;
+  }
+  const double fx = floor(__dmul_rn(__dsub_rn(__dsub_rn(px, S.half_res), S.ox), S.res_inv));
+  const double fy = floor(__dmul_rn(__dsub_rn(__dsub_rn(py, S.half_res), S.oy), S.res_inv));
+  const double fz = floor(__dmul_rn(__dsub_rn(__dsub_rn(pz, S.half_res), S.oz), S.res_inv));
+  const double dx = __dmul_rn(__dsub_rn(px, __dadd_rn(__dmul_rn(__dadd_rn(fx, 0.5), S.res), S.ox)), S.res_inv);
+  const double dy = __dmul_rn(__dsub_rn(py, __dadd_rn(__dmul_rn(__dadd_rn(fy, 0.5), S.res), S.oy)), S.res_inv);
+  const double dz = __dmul_rn(__dsub_rn(pz, __dadd_rn(__dmul_rn(__dadd_rn(fz, 0.5), S.res), S.oz)), S.res_inv);
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  const int x0 = max(min(ix, S.nx - 1), 0), x1 = max(min(ix + 1, S.nx - 1), 0);
+  const int y0 = max(min(iy, S.ny - 1), 0), y1 = max(min(iy + 1, S.ny - 1), 0);
+  const int z0 = max(min(iz, S.nz - 1), 0), z1 = max(min(iz + 1, S.nz - 1), 0);
+  const int64_t sx = (int64_t)S.ny * S.nz, sy = S.nz;
+  const double* D = S.dist;
+  const double v000 = D[x0 * sx + y0 * sy + z0], v001 = D[x0 * sx + y0 * sy + z1];
+  const double v010 = D[x0 * sx + y1 * sy + z0], v011 = D[x0 * sx + y1 * sy + z1];
+  const double v100 = D[x1 * sx + y0 * sy + z0], v101 = D[x1 * sx + y0 * sy + z1];
+  const double v110 = D[x1 * sx + y1 * sy + z0], v111 = D[x1 * sx + y1 * sy + z1];
+  // unfused, reference order: results are bit-identical to the CPU path
+  const double ex = __dsub_rn(1.0, dx), ey = __dsub_rn(1.0, dy), ez = __dsub_rn(1.0, dz);
+  const double v00 = __dadd_rn(__dmul_rn(ex, v000), __dmul_rn(dx, v100));
+  const double v01 = __dadd_rn(__dmul_rn(ex, v001), __dmul_rn(dx, v101));
+  const double v10 = __dadd_rn(__dmul_rn(ex, v010), __dmul_rn(dx, v110));
+  const double v11 = __dadd_rn(__dmul_rn(ex, v011), __dmul_rn(dx, v111));
+  const double v0 = __dadd_rn(__dmul_rn(ey, v00), __dmul_rn(dy, v10));
+  const double v1 = __dadd_rn(__dmul_rn(ey, v01), __dmul_rn(dy, v11));
+  dist[i] = __dadd_rn(__dmul_rn(ez, v0), __dmul_rn(dz, v1));
+  grad[3 * i + 2] = __dmul_rn(__dsub_rn(v1, v0), S.res_inv);
+  grad[3 * i + 1] = __dmul_rn(
+      __dadd_rn(__dmul_rn(ez, __dsub_rn(v10, v00)), __dmul_rn(dz, __dsub_rn(v11, v01))), S.res_inv);
+  double g0 = __dmul_rn(__dmul_rn(ez, ey), __dsub_rn(v100, v000));
+  g0 = __dadd_rn(g0, __dmul_rn(__dmul_rn(ez, dy), __dsub_rn(v110, v010)));
+  g0 = __dadd_rn(g0, __dmul_rn(__dmul_rn(dz, ey), __dsub_rn(v101, v001)));
+  g0 = __dadd_rn(g0, __dmul_rn(__dmul_rn(dz, dy), __dsub_rn(v111, v011)));
+  grad[3 * i] = __dmul_rn(g0, S.res_inv);
+}
+
+cudaError_t launch_query(const SdfView& S, const double* pos_dev, int64_t n, double* dist_dev, double* grad_dev,
+                         unsigned long long* oob_dev, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_query<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S, pos_dev, n, dist_dev, grad_dev, oob_dev);
+  return cudaGetLastError();
+}
+
+}  // namespace gtop
