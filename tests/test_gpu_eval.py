@@ -1,0 +1,191 @@
+"""GPU cost+gradient kernel vs the CPU oracle on identical inputs (parity gate: 1e-9 relative).
+
+Reference behaviour under test: GradTrajOptimizer::getCostAndGradient / costFunc
+(src/grad_traj_optimizer.cpp:281-448, 554-562 upstream) with the rulings of SURVEY §9.
+Parity definition: e_c = |c - c_ref| / |c_ref|, e_g = ||g - g_ref||_inf / ||g_ref||_inf,
+max over the batch <= 1e-9 (fp64 SDF)."""
+import numpy as np
+import pytest
+
+from common import (map_a_batch, map_a_oracle, oracle_map_from_cfg, oracle_problem, rel_cost_err, rel_grad_err)
+from grad_traj_optimization_b200 import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9  # north_star tolerance for fp64 SDF storage
+
+
+def _api():
+    from grad_traj_optimization_b200 import api
+    return api
+
+
+def _gpu_map_from_oracle(om):
+    gm = _api().SdfMap(om.origin, om.resolution, om.size)
+    gm.upload_distance(om.distance())
+    return gm
+
+
+def _starts(opt, n_starts, seed):
+    lb, ub = opt.bounds()
+    return fx.multi_starts(opt.x0(), lb, ub, n_starts, seed=seed)
+
+
+@pytest.mark.parametrize("name", ["text_input", "opti_node"])
+@pytest.mark.parametrize("step", [1, 2])
+def test_fixture_dense_path_parity(gtop_lib, name, step):
+    """Drop-in path: the oracle's L, R, Df, segment_time go through gtop_problems_create_dense."""
+    api = _api()
+    cfg = fx.load_cfg(name)
+    om = oracle_map_from_cfg(cfg)
+    opt = oracle_problem(cfg, om, cfg["waypoints"])
+    gm = _gpu_map_from_oracle(om)
+    ps = api.ProblemSet.from_dense(opt.seg_time(), opt.L(), opt.R(), opt.Df(), api.make_params(cfg["params"]))
+    X = _starts(opt, 64, seed=11)
+    c_ref, g_ref, oob_ref, _ = opt.eval_batch(X, step)
+    c, g, oob = ps.eval_host(gm, X, step=step, starts_per_problem=X.shape[0])
+    assert oob == oob_ref
+    assert rel_cost_err(c, c_ref).max() <= TOL
+    assert rel_grad_err(g, g_ref).max() <= TOL
+
+
+@pytest.mark.parametrize("name", ["text_input", "opti_node"])
+def test_fixture_native_setup_parity(gtop_lib, name):
+    """Native path: waypoints -> gtop_problems_create_from_paths (own O(m) set-up) vs the oracle's
+    dense LU set-up; matrices agree to 1e-12 and the objective to 1e-9."""
+    api = _api()
+    cfg = fx.load_cfg(name)
+    om = oracle_map_from_cfg(cfg)
+    opt = oracle_problem(cfg, om, cfg["waypoints"])
+    gm = _gpu_map_from_oracle(om)
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+    assert (ps.m, ps.n) == (opt.m, opt.n)
+    assert np.array_equal(ps.seg_time()[0], opt.seg_time())
+    assert np.array_equal(ps.x0()[0], opt.x0())
+    lb, ub = opt.bounds()
+    assert np.array_equal(ps.bounds()[0][0], lb) and np.array_equal(ps.bounds()[1][0], ub)
+    assert np.array_equal(ps.Df(), opt.Df())
+    L, R = ps.dense_L(), ps.dense_R()
+    assert np.abs(L - opt.L()).max() <= 1e-12 * np.abs(opt.L()).max()
+    assert np.abs(R - opt.R()).max() <= 1e-12 * np.abs(opt.R()).max()
+    X = _starts(opt, 32, seed=5)
+    c_ref, g_ref, _, _ = opt.eval_batch(X, 2)
+    c, g, _ = ps.eval_host(gm, X, step=2, starts_per_problem=X.shape[0])
+    assert rel_cost_err(c, c_ref).max() <= TOL
+    assert rel_grad_err(g, g_ref).max() <= TOL
+    assert np.abs(ps.coeff_from_x(X[3]) - opt.coeff_from_x(X[3])).max() <= 1e-11
+
+
+@pytest.mark.parametrize("m,n_problems,n_starts,ns", [(6, 16, 64, 30),   # config 2 shape (B = 1,024)
+                                                      (10, 4, 256, 30),  # config 3 shape, 4 waypoint sets
+                                                      (30, 2, 8, 200),   # config 5 shape
+                                                      (2, 3, 5, 30), (17, 2, 3, 45), (33, 1, 4, 7)])
+def test_map_a_batches_parity(gtop_lib, m, n_problems, n_starts, ns):
+    api = _api()
+    om, _ = map_a_oracle()
+    gm = _gpu_map_from_oracle(om)
+    wps, X = map_a_batch(m, n_problems, n_starts)
+    prm = dict(fx.PARAMS_OPTI, samples_per_segment=ns)
+    ps = api.ProblemSet.from_paths(wps, api.make_params(prm))
+    c, g, oob = ps.eval_host(gm, X, step=2, starts_per_problem=n_starts)
+    oob_ref = 0
+    for p in range(n_problems):
+        opt = oracle_problem(prm, om, wps[p])
+        sl = slice(p * n_starts, (p + 1) * n_starts)
+        c_ref, g_ref, o, _ = opt.eval_batch(X[sl], 2)
+        oob_ref += o
+        assert rel_cost_err(c[sl], c_ref).max() <= TOL, "problem %d" % p
+        assert rel_grad_err(g[sl], g_ref).max() <= TOL, "problem %d" % p
+    assert oob == oob_ref
+
+
+def test_device_path_equals_host_path_and_split_invariance(gtop_lib):
+    """Device-resident evaluation, the host (copy-in/out) path and any contiguous split of the batch
+    (the multi-GPU partition rule) give bit-identical per-trajectory results."""
+    import torch
+    api = _api()
+    om, _ = map_a_oracle()
+    gm = _gpu_map_from_oracle(om)
+    wps, X = map_a_batch(10, 3, 40)
+    ps = api.ProblemSet.from_paths(wps, api.make_params(fx.PARAMS_OPTI))
+    c_h, g_h, _ = ps.eval_host(gm, X, starts_per_problem=40)
+    Xd = torch.from_numpy(X).cuda()
+    cd = torch.empty(X.shape[0], dtype=torch.float64, device="cuda")
+    gd = torch.empty_like(Xd)
+    torch.cuda.synchronize()
+    ps.eval_device(gm, Xd, cd, gd, starts_per_problem=40, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(cd.cpu().numpy(), c_h) and np.array_equal(gd.cpu().numpy(), g_h)
+    for parts in (2, 4, 8):
+        bounds = np.linspace(0, X.shape[0], parts + 1).astype(int)
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            c_p, g_p, _ = ps.eval_host(gm, X[lo:hi], traj_offset=int(lo), starts_per_problem=40)
+            assert np.array_equal(c_p, c_h[lo:hi]) and np.array_equal(g_p, g_h[lo:hi])
+
+
+def test_out_of_map_samples_follow_ruling_h3(gtop_lib):
+    """Samples outside the map: dist = -1, grad = 0, counted; parity still holds."""
+    api = _api()
+    cfg = fx.load_cfg("text_input")
+    om = oracle_map_from_cfg(cfg)
+    opt = oracle_problem(cfg, om, cfg["waypoints"])
+    gm = _gpu_map_from_oracle(om)
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+    lb, ub = opt.bounds()
+    X = fx.multi_starts(opt.x0(), lb, ub, 16, seed=3, sigma=(3.0, 4.0, 5.0))  # wild starts leave the 5 m tall map
+    c_ref, g_ref, oob_ref, _ = opt.eval_batch(X, 2)
+    c, g, oob = ps.eval_host(gm, X, starts_per_problem=16)
+    assert oob_ref > 0 and oob == oob_ref
+    assert rel_cost_err(c, c_ref).max() <= TOL
+    assert rel_grad_err(g, g_ref).max() <= TOL
+
+
+def test_small_collision_weight_skips_sample_pass(gtop_lib):
+    """|wc| < 1e-4 breaks out of the segment loop (:346)."""
+    api = _api()
+    cfg = fx.load_cfg("opti_node")
+    om = oracle_map_from_cfg(cfg)
+    prm = dict(cfg["params"], wc=5e-5)
+    opt = oracle_problem(prm, om, cfg["waypoints"])
+    gm = _gpu_map_from_oracle(om)
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(prm))
+    X = _starts(opt, 4, seed=2)
+    c_ref, g_ref, _, _ = opt.eval_batch(X, 2)
+    c, g, _ = ps.eval_host(gm, X, starts_per_problem=4)
+    assert rel_cost_err(c, c_ref).max() <= TOL and rel_grad_err(g, g_ref).max() <= TOL
+
+
+def test_objective_callback_matches_batch(gtop_lib):
+    """gtop_objective (NLopt nlopt_func signature) == one row of the batched evaluation."""
+    api = _api()
+    cfg = fx.load_cfg("opti_node")
+    om = oracle_map_from_cfg(cfg)
+    opt = oracle_problem(cfg, om, cfg["waypoints"])
+    gm = _gpu_map_from_oracle(om)
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+    X = _starts(opt, 3, seed=8)
+    c, g, _ = ps.eval_host(gm, X, starts_per_problem=3)
+    obj = api.Objective(gm, ps, 0, step=2)
+    for i in range(3):
+        ci, gi = obj(X[i])
+        assert ci == c[i] and np.array_equal(gi, g[i])
+    assert obj.evals == 3
+    c_ref, g_ref, _ = opt.eval(X[1], 2)
+    assert abs(obj(X[1])[0] - c_ref) <= TOL * abs(c_ref)
+
+
+def test_golden_vectors(gtop_lib):
+    """Committed oracle outputs (tests/golden/make_golden.py) — parity without the live oracle."""
+    import os
+    api = _api()
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "fixtures_eval.npz"))
+    for name in ("text_input", "opti_node"):
+        cfg = fx.load_cfg(name)
+        gm = api.SdfMap(cfg["map_origin"], cfg["resolution"], cfg["map_size"])
+        gm.update(cfg["obstacles"])
+        ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+        X = gold[name + "_X"]
+        for step in (1, 2):
+            c, g, _ = ps.eval_host(gm, X, step=step, starts_per_problem=X.shape[0])
+            assert rel_cost_err(c, gold["%s_cost_step%d" % (name, step)]).max() <= TOL
+            assert rel_grad_err(g, gold["%s_grad_step%d" % (name, step)]).max() <= TOL
