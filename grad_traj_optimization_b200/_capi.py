@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgtop_b200.so")
+LIB_PATH = os.environ.get("GTOP_B200_LIB") or os.path.join(_HERE, "libgtop_b200.so")  # env override: kernel A/B builds
 
 # every symbol include/gtop_c.h declares (tests check that the library exports all of them)
 SYMBOLS = (

@@ -7,14 +7,19 @@
 //       with SDFMap::getDistWithGradTrilinear (src/sdf_map.cpp:185-242) gathers from HBM/L2
 //   (c) coefficient map c = L d (getCoefficientFromDerivative :253-279) in per-segment 6x6 blocks
 //
-// Work decomposition (v2): ONE WARP PER TRAJECTORY, no block-level barrier anywhere.  The warp walks
-// the trajectory's segments; inside a segment one lane = one sample (30 of 32 lanes busy), so the
-// lanes of a gather instruction hit neighbouring voxels (samples are 1/30 of a segment apart: a
-// handful of 128-B lines of the z-fastest grid per load instruction).  Per-sample work stays in
-// registers; the 3x6 per-segment accumulators U[a][i] = sum_k (sA_ak tau_ik + sB_ak tau'_ik) and
-// the cost are reduced across the warp with a transposing shuffle reduction (21 exchanges for 19
-// values instead of 19 x 5 butterflies) and projected once through the segment's 6x6 block —
-// O(m N_s) instead of the reference's dense O(m^2 N_s) products (:376-381).
+// Work decomposition (v4): a QUARTER-WARP (8 lanes) PER TRAJECTORY, four trajectories per warp
+// walking their segments in lock-step; there is no block-level barrier anywhere.  Inside a segment
+// lane j of the quarter takes samples j, j+8, j+16, ... (4 per lane at N_s = 30), so
+//   * the 8 lanes of a quarter gather from 8 consecutive samples (~0.5 m of path: 3-4 128-B lines
+//     of the z-fastest grid per 128-bit load instruction),
+//   * every lane has several independent sample iterations in flight (latency hiding by ILP; the
+//     kernel needs ~128 registers, i.e. 16 warps/SM),
+//   * the per-segment serial steps — coefficient staging, the cross-lane reduction of the 3x6
+//     accumulators U[a][i] = sum_k (sA_ak tau_ik + sB_ak tau'_ik), the projection through the
+//     segment's 6x6 block — are paid once per FOUR segments and the reduction spans only 8 lanes
+//     (18 exchanges of a transposing shuffle reduction instead of 19 x 5 butterflies).
+// The projection through the 6x6 block replaces the reference's dense per-sample products
+// (:376-381): O(m N_s) work instead of O(m^2 N_s).
 //
 // Rounding discipline: everything that feeds the float truncation of position /
 // velocity (:457-485) and the voxel index / diff arithmetic (sdf_map.cpp:201-209) is evaluated in
@@ -29,7 +34,11 @@
 
 namespace gtop {
 
-constexpr int kWarpsPerCta = 4;
+#ifndef GTOP_EVAL_MINB
+#define GTOP_EVAL_MINB 1
+#endif
+constexpr int kMaxWarpsPerCta = 4;
+constexpr int kTrajPerWarp = 4;  // quarter-warps
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double f32_round_trip(double x) { return (double)__double2float_rn(x); }
@@ -58,15 +67,20 @@ __device__ __forceinline__ bool sdf_trilinear(const SdfView& S, double px, doubl
   // clamped corner indices (getDistance(Vector3i) :166-174)
   const int x0 = max(min(ix, S.nx - 1), 0), x1 = max(min(ix + 1, S.nx - 1), 0);
   const int y0 = max(min(iy, S.ny - 1), 0), y1 = max(min(iy + 1, S.ny - 1), 0);
-  const int z0 = max(min(iz, S.nz - 1), 0), z1 = max(min(iz + 1, S.nz - 1), 0);
+  // z-corners: one aligned 128-bit load per (x,y) column from the z-pair copy, pair[z] =
+  // (D[z], D[min(z+1,nz-1)]).  clamp(iz)/clamp(iz+1) (:166-174) differ from (zc, zc+1) only for
+  // iz = -1 (both corners are D[0]); iz <= nz-1 always holds inside the map.
+  const int zc = max(iz, 0);
+  const bool zlow = iz < 0;
   const int syz = S.ny * S.nz;
-  const double* __restrict__ D = S.dist;
+  const double2* __restrict__ D = S.pair + zc;
   const int o00 = x0 * syz + y0 * S.nz, o01 = x0 * syz + y1 * S.nz;  // nvox < 2^31 checked on the host
   const int o10 = x1 * syz + y0 * S.nz, o11 = x1 * syz + y1 * S.nz;
-  const double v000 = __ldg(D + o00 + z0), v001 = __ldg(D + o00 + z1);
-  const double v010 = __ldg(D + o01 + z0), v011 = __ldg(D + o01 + z1);
-  const double v100 = __ldg(D + o10 + z0), v101 = __ldg(D + o10 + z1);
-  const double v110 = __ldg(D + o11 + z0), v111 = __ldg(D + o11 + z1);
+  const double2 q00 = __ldg(D + o00), q01 = __ldg(D + o01), q10 = __ldg(D + o10), q11 = __ldg(D + o11);
+  const double v000 = q00.x, v001 = zlow ? q00.x : q00.y;
+  const double v010 = q01.x, v011 = zlow ? q01.x : q01.y;
+  const double v100 = q10.x, v101 = zlow ? q10.x : q10.y;
+  const double v110 = q11.x, v111 = zlow ? q11.x : q11.y;
   // x-lerps; the x-differences feed grad x
   const double e00 = v100 - v000, e01 = v101 - v001, e10 = v110 - v010, e11 = v111 - v011;
   const double v00 = fma(dx, e00, v000), v01 = fma(dx, e01, v001);
@@ -97,49 +111,51 @@ __device__ __forceinline__ void xreduce_step(double (&v)[20], int lane, int bit)
   }
 }
 
-// per-warp shared memory (doubles):
+// per-trajectory (quarter-warp) shared memory, in doubles:
 //   Wd   [3][nrow]   boundary derivatives per axis in waypoint order (nrow = 3(m+1))
 //   ga   [3][nrow]   collision gradient accumulated in the same order
-//   cb   [32]        staging: c[3][6] + e[3][4] per segment; then the 19 reduced sums
-__host__ __device__ inline int warp_smem_doubles(int m) { return 2 * 9 * (m + 1) + 32; }
+//   cb   [32]        c[3][6] + e[3][4] of the current segment
+//   rs   [20]        the 19 reduced sums of the current segment
+__host__ __device__ inline int traj_smem_doubles(int m) { return 2 * 9 * (m + 1) + 32 + 20; }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, GTOP_EVAL_MINB)
 k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_problems, EvalScalars E,
             const double* __restrict__ X, int64_t B, int64_t traj_offset, int64_t starts_per_problem,
             double* __restrict__ cost_out, double* __restrict__ grad_out, unsigned long long* __restrict__ oob_counter) {
   extern __shared__ double smem[];
   const int m = PL.m, P = PL.P, n = PL.n, nrow = 3 * (m + 1);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* Wd = smem + warp * warp_smem_doubles(m);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int q = lane >> 3, j = lane & 7;  // trajectory slot of the warp, lane within the quarter
+
+  const int64_t b_raw = ((int64_t)blockIdx.x * wpc + warp) * kTrajPerWarp + q;
+  if (b_raw - q >= B) return;              // the whole warp is past the end
+  const bool live = b_raw < B;             // ragged tail: dead quarters shadow the last trajectory
+  const int64_t b = live ? b_raw : B - 1;  // (same control flow, outputs suppressed)
+
+  double* Wd = smem + (warp * kTrajPerWarp + q) * traj_smem_doubles(m);
   double* ga = Wd + 3 * nrow;
   double* cb = ga + 3 * nrow;
-
-  const int64_t b = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-  if (b >= B) return;  // whole warp exits; there is no block-level synchronisation in this kernel
+  double* rs = cb + 32;
 
   const int64_t pid = ((traj_offset + b) / starts_per_problem) % num_problems;
   const double* __restrict__ pr = prob + pid * (int64_t)PL.stride;
   const double* __restrict__ x = X + b * n;
 
   // ---- 1. boundary derivatives in waypoint order; clear the gradient accumulators ---------------
-  for (int j = lane; j < P; j += 32) {
+  for (int jj = j; jj < P; jj += 8) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) Wd[a * nrow + 3 + j] = x[a * P + j];
+    for (int a = 0; a < 3; ++a) Wd[a * nrow + 3 + jj] = x[a * P + jj];
   }
-  if (lane < 18) {
-    const int a = lane / 6, q = lane % 6;
-    Wd[a * nrow + (q < 3 ? q : 3 * m + (q - 3))] = pr[PL.off_Df + lane];
+  for (int o = j; o < 18; o += 8) {
+    const int a = o / 6, r = o % 6;
+    Wd[a * nrow + (r < 3 ? r : 3 * m + (r - 3))] = pr[PL.off_Df + o];
   }
-  for (int j = lane; j < 3 * nrow; j += 32) ga[j] = 0.0;
+  for (int jj = j; jj < 3 * nrow; jj += 8) ga[jj] = 0.0;
   __syncwarp();
 
-  // lane roles for the per-segment 18-wide steps: (axis, index)
-  const int la = (lane < 18) ? lane / 6 : 0, li = (lane < 18) ? lane % 6 : 0;
-  // which of the 19 reduced sums this lane ends up holding after the transposing reduction
-  const int b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
-  const int sub = 3 * b2 + 2 * b1 + b0;
-  const bool red_valid = !((b1 & b0) | (b2 & b1));          // sub in {0,1,2,3,4}
-  const int red_idx = 10 * ((lane >> 4) & 1) + 5 * ((lane >> 3) & 1) + sub;
+  // which reduced sums this lane holds after the 8-lane transposing reduction (3 per lane)
+  const int red_base = 10 * ((j >> 2) & 1) + 5 * ((j >> 1) & 1) + 3 * (j & 1);
+  const int red_cnt = (j & 1) ? 2 : 3;  // odd lanes hold (3,4,pad) of their group of five
 
   double Jc_total = 0.0;
   unsigned oob = 0;
@@ -149,21 +165,24 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
   if (!E.skip_collision) {
     for (int s = 0; s < m; ++s) {
       const double* __restrict__ Li = pr + PL.off_Linv + s * 36;
+      const double* __restrict__ LiT = pr + PL.off_LinvT + s * 36;
       // ---- coefficients c[a][i] = sum_r Linv[i][r] * dseg[a][r], summed in ascending dense-column
       // order of L (start derivatives first, except for the last segment whose end derivatives live
       // in columns 3..5 of d) with unfused mul/add — the same 6-term sum as `L * d` (:273).
-      if (lane < 18) {
-        const double* w0 = Wd + la * nrow + 3 * s;  // p0,v0,a0,pT,vT,aT contiguous in waypoint order
+      const bool last = (s == m - 1);
+#pragma unroll
+      for (int o = j; o < 18; o += 8) {
+        const int a = o / 6, i = o % 6;
+        const double* w0 = Wd + a * nrow + 3 * s;  // p0,v0,a0,pT,vT,aT contiguous in waypoint order
         double p[6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) p[r] = __dmul_rn(Li[li * 6 + r], w0[r]);
-        const bool last = (s == m - 1);
+        for (int r = 0; r < 6; ++r) p[r] = __dmul_rn(LiT[r * 6 + i], w0[r]);
         const double q0 = last ? p[3] : p[0], q1 = last ? p[4] : p[1], q2 = last ? p[5] : p[2];
         const double q3 = last ? p[0] : p[3], q4 = last ? p[1] : p[4], q5 = last ? p[2] : p[5];
         const double c = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(q0, q1), q2), q3), q4), q5);
-        cb[lane] = c;
+        cb[o] = c;
         // e_k = k*c_k for the velocity polynomial (2*coeff(s,2), 3*coeff(s,3), ... :477-485)
-        if (li >= 2) cb[18 + la * 4 + (li - 2)] = __dmul_rn((double)li, c);
+        if (i >= 2) cb[18 + a * 4 + (i - 2)] = __dmul_rn((double)i, c);
       }
       __syncwarp();
 
@@ -175,7 +194,7 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
 #pragma unroll
       for (int i = 0; i < 20; ++i) v[i] = 0.0;
 
-      for (int k = lane; k < ns; k += 32) {
+      for (int k = j; k < ns; k += 8) {
         const double t = tt[k], t2 = tt[ns_cap + k], t3 = tt[2 * ns_cap + k], t4 = tt[3 * ns_cap + k],
                      t5 = tt[4 * ns_cap + k];
         double pos[3], vel[3];
@@ -223,65 +242,73 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
         }
       }
 
-      // ---- transposing warp reduction: 20 -> 10 -> 5 -> 3 -> 2 -> 1 values per lane ---------------
-      xreduce_step<10>(v, lane, 16);
-      xreduce_step<5>(v, lane, 8);
+      // ---- transposing reduction inside the quarter: 20 -> 10 -> 5 -> 3 values per lane ----------
+      xreduce_step<10>(v, lane, 4);
+      xreduce_step<5>(v, lane, 2);
       v[5] = 0.0;
-      xreduce_step<3>(v, lane, 4);
-      v[3] = 0.0;
-      xreduce_step<2>(v, lane, 2);
-      xreduce_step<1>(v, lane, 1);
-      __syncwarp();  // everybody is done reading c/e from cb
-      if (red_valid && red_idx < 19) cb[red_idx] = v[0];
+      xreduce_step<3>(v, lane, 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (i < red_cnt && red_base + i < 19) rs[red_base + i] = v[i];
       __syncwarp();
-      Jc_total = fma(cb[18], dt, Jc_total);
+      Jc_total = fma(rs[18], dt, Jc_total);
       // ---- back-projection through the segment block: g[a][r] = sum_i U[a][i]*Linv[i][r] (T*Ldp, :378-379)
-      if (lane < 18) {
+#pragma unroll
+      for (int o = j; o < 18; o += 8) {
+        const int a = o / 6, r = o % 6;
         double acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) acc = fma(cb[la * 6 + i], Li[i * 6 + li], acc);
-        ga[la * nrow + 3 * s + li] += acc * dt;
+        for (int i = 0; i < 6; ++i) acc = fma(rs[a * 6 + i], Li[i * 6 + r], acc);
+        ga[a * nrow + 3 * s + r] += acc * dt;
       }
       __syncwarp();
     }
   }
   if (oob_counter != nullptr) {
-    oob = __reduce_add_sync(kFull, oob);
+    oob = __reduce_add_sync(kFull, live ? oob : 0u);
     if (lane == 0 && oob) atomicAdd(oob_counter, (unsigned long long)oob);
   }
 
   // ---- 3. smoothness cost: banded column sums of R in waypoint order (:326-327) -------------------
   double js = 0.0;
-  for (int u = lane; u < nrow; u += 32) {
+  for (int u = j; u < nrow; u += 8) {
     const double* __restrict__ band = pr + PL.off_Rc + u * 9;
     const int base = 3 * (u / 3 - 1);
     const int j0 = base < 0 ? 3 : 0, j1 = (base + 9 > nrow) ? 6 : 9;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double* Wa = Wd + a * nrow;
-      double y = 0.0;
-      for (int j = j0; j < j1; ++j) y = fma(Wa[base + j], band[j], y);
-      js = fma(y, Wa[u], js);
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+    for (int jj = j0; jj < j1; ++jj) {
+      const double bv = band[jj];
+      y0 = fma(Wd[base + jj], bv, y0);
+      y1 = fma(Wd[nrow + base + jj], bv, y1);
+      y2 = fma(Wd[2 * nrow + base + jj], bv, y2);
     }
+    js = fma(y0, Wd[u], js);
+    js = fma(y1, Wd[nrow + u], js);
+    js = fma(y2, Wd[2 * nrow + u], js);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) js += __shfl_xor_sync(kFull, js, o);
+  for (int o = 4; o > 0; o >>= 1) js += __shfl_xor_sync(kFull, js, o);
 
   // ---- 4. outputs (:417-431) ----------------------------------------------------------------------
-  double* __restrict__ gout = grad_out + b * n;
-  for (int j = lane; j < P; j += 32) {
-    const double* __restrict__ band = pr + PL.off_Rg + j * 9;  // 2 Rfp' df + 2 Rpp dp row (:330-332)
-    const int base = j - j % 3;                                // 3*(wp-1), wp = j/3 + 1
+  if (live) {
+    double* __restrict__ gout = grad_out + b * n;
+    for (int jj = j; jj < P; jj += 8) {
+      const double* __restrict__ band = pr + PL.off_Rg + jj * 9;  // 2 Rfp' df + 2 Rpp dp row (:330-332)
+      const double* Wb = Wd + (jj - jj % 3);                      // 3*(wp-1), wp = jj/3 + 1
+      double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double* Wa = Wd + a * nrow + base;
-      double gs = 0.0;
-#pragma unroll
-      for (int jj = 0; jj < 9; ++jj) gs = fma(Wa[jj], band[jj], gs);
-      gout[a * P + j] = (E.ws * (2.0 * gs) + E.wc * ga[a * nrow + 3 + j]) + 1e-5;
+      for (int t = 0; t < 9; ++t) {
+        const double bv = band[t];
+        g0 = fma(Wb[t], bv, g0);
+        g1 = fma(Wb[nrow + t], bv, g1);
+        g2 = fma(Wb[2 * nrow + t], bv, g2);
+      }
+      gout[jj] = (E.ws * (2.0 * g0) + E.wc * ga[3 + jj]) + 1e-5;
+      gout[P + jj] = (E.ws * (2.0 * g1) + E.wc * ga[nrow + 3 + jj]) + 1e-5;
+      gout[2 * P + jj] = (E.ws * (2.0 * g2) + E.wc * ga[2 * nrow + 3 + jj]) + 1e-5;
     }
+    if (j == 0) cost_out[b] = E.ws * js + E.wc * (E.alpha * Jc_total) + 1e-3;
   }
-  if (lane == 0) cost_out[b] = E.ws * js + E.wc * (E.alpha * Jc_total) + 1e-3;
 }
 
 cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
@@ -290,14 +317,19 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
                         int max_ctas, cudaStream_t stream) {
   (void)max_ctas;
   if (B <= 0) return cudaSuccess;
-  const size_t smem = sizeof(double) * (size_t)warp_smem_doubles(PL.m) * kWarpsPerCta;
+  // warps per CTA: as many as keep the CTA's shared memory modest (4 CTAs/SM at 16 warps/SM)
+  const size_t per_warp = sizeof(double) * (size_t)traj_smem_doubles(PL.m) * kTrajPerWarp;
+  int wpc = kMaxWarpsPerCta;
+  while (wpc > 1 && per_warp * wpc > 48 * 1024) wpc >>= 1;
+  const size_t smem = per_warp * wpc;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_eval_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const int64_t grid = (B + kWarpsPerCta - 1) / kWarpsPerCta;
-  k_eval_traj<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset,
-                                                                   starts_per_problem, cost, grad, oob_counter);
+  const int64_t per_cta = (int64_t)wpc * kTrajPerWarp;
+  const int64_t grid = (B + per_cta - 1) / per_cta;
+  k_eval_traj<<<(unsigned)grid, wpc * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset,
+                                                          starts_per_problem, cost, grad, oob_counter);
   return cudaGetLastError();
 }
 

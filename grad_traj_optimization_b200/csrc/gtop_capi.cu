@@ -21,6 +21,7 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
                         int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
                         int max_ctas, cudaStream_t stream);
 cudaError_t launch_fill(double* dist, uint8_t* occ, int64_t n, double dval, cudaStream_t st);
+cudaError_t launch_build_pairs(const double* dist, double2* pair, int64_t n, int nz, cudaStream_t st);
 cudaError_t launch_set_occupancy(const SdfView& S, uint8_t* occ, const double* pts_dev, int64_t n, cudaStream_t st);
 cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t* boxes_dev, int64_t n,
                              cudaStream_t st);
@@ -57,6 +58,7 @@ struct gtop_sdf {
   double origin[3], map_size[3];
   int64_t nvox = 0;
   double* dist = nullptr;
+  double2* pair = nullptr;  // z-pair copy of dist, rebuilt whenever dist changes
   uint8_t* occ = nullptr;
   int32_t *d1 = nullptr, *d2 = nullptr;
   cudaStream_t stream = nullptr;
@@ -155,6 +157,10 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
       return fail(GTOP_E_INVALID, "grid dimension out of range [1, 16384]");
     }
   }
+  if ((int64_t)g[0] * g[1] * g[2] > 2147483647LL) {
+    delete s;
+    return fail(GTOP_E_INVALID, "more than 2^31-1 voxels");
+  }
   SdfView& v = s->view;
   v.nx = g[0], v.ny = g[1], v.nz = g[2];
   v.ox = origin[0], v.oy = origin[1], v.oz = origin[2];
@@ -164,6 +170,7 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
   v.hiz = (origin[2] + map_size[2]) - 1e-4;  // :62-63 with max_range = origin + map_size (:12)
   s->nvox = (int64_t)g[0] * g[1] * g[2];
   cudaError_t e = cudaMalloc(&s->dist, sizeof(double) * s->nvox);
+  if (e == cudaSuccess) e = cudaMalloc(&s->pair, sizeof(double2) * s->nvox);
   if (e == cudaSuccess) e = cudaMalloc(&s->occ, s->nvox);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
@@ -172,8 +179,10 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
     return fail(GTOP_E_ALLOC, std::string("sdf allocation: ") + cudaGetErrorString(e));
   }
   v.dist = s->dist;
+  v.pair = s->pair;
   CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));  // sdf_map.cpp:22-23
-  ++g_launches;
+  CU(launch_build_pairs(s->dist, s->pair, s->nvox, v.nz, s->stream));
+  g_launches += 2;
   CU(cudaStreamSynchronize(s->stream));
   *out = s;
   return GTOP_OK;
@@ -182,7 +191,7 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
 int gtop_sdf_destroy(gtop_sdf* s) {
   if (!s) return GTOP_OK;
   cudaSetDevice(s->device);
-  cudaFree(s->dist), cudaFree(s->occ), cudaFree(s->d1), cudaFree(s->d2);
+  cudaFree(s->dist), cudaFree(s->pair), cudaFree(s->occ), cudaFree(s->d1), cudaFree(s->d2);
   for (auto& e : s->ev)
     if (e) cudaEventDestroy(e);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -200,7 +209,8 @@ int gtop_sdf_reset(gtop_sdf* s) {
   REQUIRE(s, "null sdf");
   CU(cudaSetDevice(s->device));
   CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));
-  ++g_launches;
+  CU(launch_build_pairs(s->dist, s->pair, s->nvox, s->view.nz, s->stream));
+  g_launches += 2;
   CU(cudaStreamSynchronize(s->stream));
   return GTOP_OK;
 }
@@ -244,7 +254,8 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
     if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("edt scratch: ") + cudaGetErrorString(e));
   }
   CU(launch_edt(s->occ, s->d1, s->d2, s->dist, s->view.nx, s->view.ny, s->view.nz, s->view.res, s->stream, s->ev));
-  g_launches += 3;
+  CU(launch_build_pairs(s->dist, s->pair, s->nvox, s->view.nz, s->stream));
+  g_launches += 4;
   CU(cudaStreamSynchronize(s->stream));
   for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&s->last_ms[i], s->ev[i], s->ev[i + 1]);
   cudaEventElapsedTime(&s->last_ms[3], s->ev[0], s->ev[3]);
@@ -267,6 +278,9 @@ int gtop_sdf_upload_distance(gtop_sdf* s, const double* host) {
   REQUIRE(s && host, "null argument");
   CU(cudaSetDevice(s->device));
   CU(cudaMemcpy(s->dist, host, sizeof(double) * s->nvox, cudaMemcpyHostToDevice));
+  CU(launch_build_pairs(s->dist, s->pair, s->nvox, s->view.nz, s->stream));
+  ++g_launches;
+  CU(cudaStreamSynchronize(s->stream));
   return GTOP_OK;
 }
 int gtop_sdf_download_occupancy(const gtop_sdf* s, int32_t* host) {

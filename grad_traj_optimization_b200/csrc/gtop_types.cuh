@@ -1,5 +1,7 @@
 // gtop_types.cuh — PODs shared by the host side of libgtop_b200 and its sm_100a kernels.
 #pragma once
+#include <vector_types.h>
+
 #include <cstdint>
 
 namespace gtop {
@@ -8,6 +10,11 @@ namespace gtop {
 // reference (sdf_map.cpp:92,97-98): z is the fastest axis.
 struct SdfView {
   const double* dist;  // nx*ny*nz fp64 distances
+  // z-pair copy of the same field: pair[i] = (dist[x,y,z], dist[x,y,min(z+1,nz-1)]) as one 16-byte
+  // element, so the two z-corners of a trilinear cell come from ONE aligned 128-bit load whatever
+  // the parity of z (z is the fastest axis).  2x the footprint (32 MB for the 200x200x50 map:
+  // still L2-resident), half the gather instructions / L1 wavefronts.
+  const double2* pair;
   int nx, ny, nz;
   double ox, oy, oz;        // origin
   double res, res_inv;      // resolution, 1/resolution (sdf_map.cpp:6-7)
@@ -26,12 +33,14 @@ struct SdfView {
 //   Rc    [3m+3][9]      column band of R in waypoint order (smoothness cost, :326-327)
 //   Rg    [3m-3][9]      band of (2 Rfp^T df + 2 Rpp dp) rows (smoothness gradient, :330-332)
 //   Df    [3][6]         fixed derivatives per axis: p0,v0,a0,pEnd,vEnd,aEnd
+//   LinvT [m][6][6]      transpose of Linv (col = power): the coefficient step reads 6 contiguous
+//                        doubles per derivative instead of a stride-6 column
 struct ProbLayout {
   int m;       // segments
   int P;       // free derivatives per axis = 3(m-1)
   int n;       // NLopt variables = 3P
   int ns_cap;  // samples_per_segment (table capacity)
-  int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df;
+  int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df, off_LinvT;
   int stride;
 };
 
@@ -49,6 +58,7 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   L.off_Rc = o, o += (3 * m + 3) * 9;
   L.off_Rg = o, o += (3 * m - 3) * 9;
   L.off_Df = o, o += 18;
+  L.off_LinvT = o, o += m * 36;
   L.stride = (o + 1) & ~1;  // keep every record 16-byte aligned
   return L;
 }

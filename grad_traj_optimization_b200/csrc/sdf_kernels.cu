@@ -37,6 +37,17 @@ __global__ void k_fill(double* __restrict__ dist, uint8_t* __restrict__ occ, int
   }
 }
 
+// z-pair copy of the distance field for the evaluation kernel's 128-bit gathers (see SdfView::pair)
+__global__ void k_build_pairs(const double* __restrict__ dist, double2* __restrict__ pair, int64_t n, int nz) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int z = (int)(i % nz);
+    const double a = dist[i];
+    const double b = (z + 1 < nz) ? dist[i + 1] : a;
+    pair[i] = make_double2(a, b);
+  }
+}
+
 __global__ void k_set_occupancy(SdfView S, uint8_t* __restrict__ occ, const double* __restrict__ pts, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -200,6 +211,11 @@ static cudaError_t launch_yx(const int32_t* d1, int32_t* d2, double* dist, int n
 
 cudaError_t launch_fill(double* dist, uint8_t* occ, int64_t n, double dval, cudaStream_t st) {
   k_fill<<<148 * 8, 256, 0, st>>>(dist, occ, n, dval);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_pairs(const double* dist, double2* pair, int64_t n, int nz, cudaStream_t st) {
+  k_build_pairs<<<148 * 16, 256, 0, st>>>(dist, pair, n, nz);
   return cudaGetLastError();
 }
 
