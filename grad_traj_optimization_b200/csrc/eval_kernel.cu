@@ -35,7 +35,7 @@
 namespace gtop {
 
 #ifndef GTOP_EVAL_MINB
-#define GTOP_EVAL_MINB 1
+#define GTOP_EVAL_MINB 4
 #endif
 constexpr int kMaxWarpsPerCta = 4;
 constexpr int kTrajPerWarp = 4;  // quarter-warps
@@ -43,58 +43,116 @@ constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double f32_round_trip(double x) { return (double)__double2float_rn(x); }
 
-// SDFMap::getDistWithGradTrilinear (sdf_map.cpp:185-242).  Out of map: dist=-1, grad=0 (H3).
+// ---- branch-free FP64 helpers for the smooth part of the sample pass (no special-case paths: the
+// library sqrt/div/exp carry slow-path branches that split the sample body into basic blocks and
+// keep the scheduler from overlapping the gather latency with arithmetic) ---------------------------
+__device__ __forceinline__ double rcp_seed(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));  // MUFU.RCP64H, ~20 good bits
+  return r;
+}
+__device__ __forceinline__ double rsqrt_seed(double a) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));  // MUFU.RSQ64H, ~20 good bits
+  return r;
+}
+// sqrt(a) for a in the normal range (a >= 1e-300): coupled Newton (Goldschmidt) + one residual step
+__device__ __forceinline__ double sqrt_pos(double a) {
+  const double y = rsqrt_seed(a);
+  double t = a * y, h = 0.5 * y;
+  double r = fma(-t, h, 0.5);
+  t = fma(t, r, t), h = fma(h, r, h);
+  r = fma(-t, h, 0.5);
+  t = fma(t, r, t), h = fma(h, r, h);
+  return fma(fma(-t, t, a), h, t);
+}
+// 1/a for a in the normal range
+__device__ __forceinline__ double rcp_pos(double a) {
+  double y = rcp_seed(a);
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+// 2^y for y in [-1000, 64]: y = k + j/64 + r, |r| <= 1/128;  2^y = 2^k * T[j] * 2^r with a degree-5
+// polynomial for 2^r (truncation 3.5e-17).  T = 2^(j/64) lives in shared memory.
+__device__ __forceinline__ double exp2_tab(double y, const double* __restrict__ T) {
+  const double kMagic = 105553116266496.0;  // 1.5 * 2^46: ulp = 1/64
+  const double z = y + kMagic;
+  const int N = __double2loint(z);            // round(y*64)
+  const double r = y - (z - kMagic);
+  double p = 1.3333558146428443e-3;           // ln2^5/5!
+  p = fma(p, r, 9.6181291076284772e-3);       // ln2^4/4!
+  p = fma(p, r, 5.5504108664821580e-2);       // ln2^3/3!
+  p = fma(p, r, 2.4022650695910071e-1);       // ln2^2/2!
+  p = fma(p, r, 6.9314718055994531e-1);       // ln2
+  const double tj = T[N & 63];
+  const double m = fma(tj * r, p, tj);        // T[j] * (1 + r*p)
+  return __hiloint2double(__double2hiint(m) + ((N >> 6) << 20), __double2loint(m));
+}
+
+// SDFMap::getDistWithGradTrilinear (sdf_map.cpp:185-242), split in two so that the caller can put
+// independent arithmetic between the 128-bit gathers and their use:
+//   sdf_gather  : in-map test, cell index / diff (reference op order, unfused), 4 x LDG.128
+//   sdf_finish  : trilinear value and gradient; out of map -> dist=-1, grad=0 (H3), branch-free
 // The gradient is returned WITHOUT the 1/resolution factor (folded into the caller's constants).
 // Interpolation is evaluated as nested lerps a + d*(b-a): the corner differences are shared between
 // the value and the gradient (25 FP64 ops instead of 46); it differs from the reference's
 // (1-d)*a + d*b form only by rounding (~1e-16 relative).
-__device__ __forceinline__ bool sdf_trilinear(const SdfView& S, double px, double py, double pz, double& dist,
-                                              double& gx, double& gy, double& gz) {
-  if (px < S.lox || py < S.loy || pz < S.loz || px > S.hix || py > S.hiy || pz > S.hiz) {
-    dist = -1.0;
-    gx = gy = gz = 0.0;
-    return false;
-  }
+struct SdfCell {
+  double2 q00, q01, q10, q11;  // (z, z+1) pairs of the four (x,y) columns
+  double dx, dy, dz;
+  bool in_map, zlow;
+};
+
+__device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double py, double pz, SdfCell& c) {
+  c.in_map = !(px < S.lox || py < S.loy || pz < S.loz || px > S.hix || py > S.hiy || pz > S.hiz);  // :55-69
   // pos_m = pos - 0.5*res; idx = floor((pos_m - origin)*res_inv)           (:201-204, :71-74)
   const double fx = floor(__dmul_rn(__dsub_rn(__dsub_rn(px, S.half_res), S.ox), S.res_inv));
   const double fy = floor(__dmul_rn(__dsub_rn(__dsub_rn(py, S.half_res), S.oy), S.res_inv));
   const double fz = floor(__dmul_rn(__dsub_rn(__dsub_rn(pz, S.half_res), S.oz), S.res_inv));
   // idx_pos = (idx + 0.5)*res + origin; diff = (pos - idx_pos)*res_inv     (:76-78, :209)
-  const double dx = __dmul_rn(__dsub_rn(px, __dadd_rn(__dmul_rn(__dadd_rn(fx, 0.5), S.res), S.ox)), S.res_inv);
-  const double dy = __dmul_rn(__dsub_rn(py, __dadd_rn(__dmul_rn(__dadd_rn(fy, 0.5), S.res), S.oy)), S.res_inv);
-  const double dz = __dmul_rn(__dsub_rn(pz, __dadd_rn(__dmul_rn(__dadd_rn(fz, 0.5), S.res), S.oz)), S.res_inv);
+  c.dx = __dmul_rn(__dsub_rn(px, __dadd_rn(__dmul_rn(__dadd_rn(fx, 0.5), S.res), S.ox)), S.res_inv);
+  c.dy = __dmul_rn(__dsub_rn(py, __dadd_rn(__dmul_rn(__dadd_rn(fy, 0.5), S.res), S.oy)), S.res_inv);
+  c.dz = __dmul_rn(__dsub_rn(pz, __dadd_rn(__dmul_rn(__dadd_rn(fz, 0.5), S.res), S.oz)), S.res_inv);
   const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-  // clamped corner indices (getDistance(Vector3i) :166-174)
+  // clamped corner indices (getDistance(Vector3i) :166-174); the clamps also keep the loads of an
+  // out-of-map sample inside the buffer, so no branch is needed around the gather
   const int x0 = max(min(ix, S.nx - 1), 0), x1 = max(min(ix + 1, S.nx - 1), 0);
   const int y0 = max(min(iy, S.ny - 1), 0), y1 = max(min(iy + 1, S.ny - 1), 0);
   // z-corners: one aligned 128-bit load per (x,y) column from the z-pair copy, pair[z] =
-  // (D[z], D[min(z+1,nz-1)]).  clamp(iz)/clamp(iz+1) (:166-174) differ from (zc, zc+1) only for
-  // iz = -1 (both corners are D[0]); iz <= nz-1 always holds inside the map.
-  const int zc = max(iz, 0);
-  const bool zlow = iz < 0;
+  // (D[z], D[min(z+1,nz-1)]).  clamp(iz)/clamp(iz+1) differ from (zc, zc+1) only for iz = -1
+  // (both corners are D[0]); iz <= nz-1 always holds inside the map.
+  const int zc = max(min(iz, S.nz - 1), 0);
+  c.zlow = iz < 0;
   const int syz = S.ny * S.nz;
   const double2* __restrict__ D = S.pair + zc;
-  const int o00 = x0 * syz + y0 * S.nz, o01 = x0 * syz + y1 * S.nz;  // nvox < 2^31 checked on the host
-  const int o10 = x1 * syz + y0 * S.nz, o11 = x1 * syz + y1 * S.nz;
-  const double2 q00 = __ldg(D + o00), q01 = __ldg(D + o01), q10 = __ldg(D + o10), q11 = __ldg(D + o11);
-  const double v000 = q00.x, v001 = zlow ? q00.x : q00.y;
-  const double v010 = q01.x, v011 = zlow ? q01.x : q01.y;
-  const double v100 = q10.x, v101 = zlow ? q10.x : q10.y;
-  const double v110 = q11.x, v111 = zlow ? q11.x : q11.y;
+  const int ox0 = x0 * syz, ox1 = x1 * syz, oy0 = y0 * S.nz, oy1 = y1 * S.nz;  // nvox < 2^31 (host check)
+  c.q00 = __ldg(D + ox0 + oy0), c.q01 = __ldg(D + ox0 + oy1);
+  c.q10 = __ldg(D + ox1 + oy0), c.q11 = __ldg(D + ox1 + oy1);
+}
+
+__device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, double& gx, double& gy, double& gz) {
+  const double v000 = c.q00.x, v001 = c.zlow ? c.q00.x : c.q00.y;
+  const double v010 = c.q01.x, v011 = c.zlow ? c.q01.x : c.q01.y;
+  const double v100 = c.q10.x, v101 = c.zlow ? c.q10.x : c.q10.y;
+  const double v110 = c.q11.x, v111 = c.zlow ? c.q11.x : c.q11.y;
   // x-lerps; the x-differences feed grad x
   const double e00 = v100 - v000, e01 = v101 - v001, e10 = v110 - v010, e11 = v111 - v011;
-  const double v00 = fma(dx, e00, v000), v01 = fma(dx, e01, v001);
-  const double v10 = fma(dx, e10, v010), v11 = fma(dx, e11, v011);
+  const double v00 = fma(c.dx, e00, v000), v01 = fma(c.dx, e01, v001);
+  const double v10 = fma(c.dx, e10, v010), v11 = fma(c.dx, e11, v011);
   // y-lerps; y-differences feed grad y
   const double f0 = v10 - v00, f1 = v11 - v01;
-  const double v0 = fma(dy, f0, v00), v1 = fma(dy, f1, v01);
+  const double v0 = fma(c.dy, f0, v00), v1 = fma(c.dy, f1, v01);
   const double h = v1 - v0;
-  dist = fma(dz, h, v0);                 // :229
-  gz = h;                                // :231
-  gy = fma(dz, f1 - f0, f0);             // :232-233
-  const double ex0 = fma(dy, e10 - e00, e00), ex1 = fma(dy, e11 - e01, e01);
-  gx = fma(dz, ex1 - ex0, ex0);          // :234-239
-  return true;
+  const double d = fma(c.dz, h, v0);                      // :229
+  const double y = fma(c.dz, f1 - f0, f0);                // :232-233
+  const double ex0 = fma(c.dy, e10 - e00, e00), ex1 = fma(c.dy, e11 - e01, e01);
+  const double x = fma(c.dz, ex1 - ex0, ex0);             // :234-239
+  dist = c.in_map ? d : -1.0;                             // :187, H3
+  gx = c.in_map ? x : 0.0;
+  gy = c.in_map ? y : 0.0;
+  gz = c.in_map ? h : 0.0;                                // :231
 }
 
 // One step of the transposing reduction: every lane holds 2*H values; lanes whose `bit` is clear
@@ -126,6 +184,11 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
   const int m = PL.m, P = PL.P, n = PL.n, nrow = 3 * (m + 1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const int q = lane >> 3, j = lane & 7;  // trajectory slot of the warp, lane within the quarter
+
+  // 2^(j/64) table for exp2_tab: the only block-level synchronisation of the kernel
+  double* xtab = smem + wpc * kTrajPerWarp * traj_smem_doubles(m);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) xtab[i] = exp2((double)i * (1.0 / 64.0));
+  __syncthreads();
 
   const int64_t b_raw = ((int64_t)blockIdx.x * wpc + warp) * kTrajPerWarp + q;
   if (b_raw - q >= B) return;              // the whole warp is past the end
@@ -201,7 +264,6 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const double* c = cb + a * 6;
-          const double* e = cb + 18 + a * 4;
           // getPositionFromCoeff (:457-465): left-to-right, unfused, then float
           double pa = __dadd_rn(c[0], __dmul_rn(c[1], t));
           pa = __dadd_rn(pa, __dmul_rn(c[2], t2));
@@ -209,6 +271,13 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
           pa = __dadd_rn(pa, __dmul_rn(c[4], t4));
           pa = __dadd_rn(pa, __dmul_rn(c[5], t5));
           pos[a] = f32_round_trip(pa);
+        }
+        SdfCell cell;
+        sdf_gather(S, pos[0], pos[1], pos[2], cell);  // 4 x LDG.128 in flight from here
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double* c = cb + a * 6;
+          const double* e = cb + 18 + a * 4;
           // getVelocityFromCoeff (:477-485)
           double va = __dadd_rn(c[1], __dmul_rn(e[0], t));
           va = __dadd_rn(va, __dmul_rn(e[1], t2));
@@ -217,18 +286,21 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
           vel[a] = f32_round_trip(va);
         }
         const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], vel[0] * vel[0]));
-        const double vnorm = sqrt(vn2) + 1e-5;  // :358
+        const double vnorm = sqrt_pos(fmax(vn2, 1e-300)) + 1e-5;  // :358 (sqrt(1e-300) is absorbed by 1e-5)
+        const double inv_vn = rcp_pos(vnorm);
 
         double dist, g[3];
-        if (!sdf_trilinear(S, pos[0], pos[1], pos[2], dist, g[0], g[1], g[2])) ++oob;
+        sdf_finish(cell, dist, g[0], g[1], g[2]);
+        oob += cell.in_map ? 0u : 1u;
 
-        const double ee = exp((E.d0 - dist) * E.inv_r);  // exp(-(d-d0)/r), :509/:514
+        // exp(-(d-d0)/r) (:509/:514) = 2^((d0-d)*log2(e)/r); d <= 10000 so clamp the exponent at -1000
+        const double ee = exp2_tab(fmax(fma(dist, E.neg_log2e_over_r, E.d0_log2e_over_r), -1000.0), xtab);
         const double ev = ee * vnorm;
         v[18] += ev;                       // cost: cd*|v| = alpha*ee*vnorm (alpha, dt applied later)
         // sA_a = gd*grad_a*cd*|v| = kA * ee^2 * vnorm * g_a      (:378, extra cd reproduced — H4)
         // sB_a = cd*v_a/|v|       = alpha * ee * v_a / vnorm     (:379)
         const double sAc = kA * (ee * ev);
-        const double sBc = E.alpha * (ee / vnorm);
+        const double sBc = E.alpha * (ee * inv_vn);
         const double tp2 = 2.0 * t, tp3 = 3.0 * t2, tp4 = 4.0 * t3, tp5 = 5.0 * t4;  // T*V (:379)
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -320,8 +392,8 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
   // warps per CTA: as many as keep the CTA's shared memory modest (4 CTAs/SM at 16 warps/SM)
   const size_t per_warp = sizeof(double) * (size_t)traj_smem_doubles(PL.m) * kTrajPerWarp;
   int wpc = kMaxWarpsPerCta;
-  while (wpc > 1 && per_warp * wpc > 48 * 1024) wpc >>= 1;
-  const size_t smem = per_warp * wpc;
+  while (wpc > 1 && per_warp * wpc + 512 > 48 * 1024) wpc >>= 1;
+  const size_t smem = per_warp * wpc + 64 * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_eval_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -98,6 +98,9 @@ static EvalScalars make_scalars(const gtop_params& p, int step) {
   E.d0 = p.d0;
   E.inv_r = 1.0 / p.r;
   E.alpha_over_r = p.alpha / p.r;
+  const double log2e = 1.4426950408889634074;
+  E.neg_log2e_over_r = -log2e / p.r;
+  E.d0_log2e_over_r = p.d0 * log2e / p.r;
   E.skip_collision = std::fabs(p.w_collision) < 1e-4 ? 1 : 0;  // :346
   return E;
 }

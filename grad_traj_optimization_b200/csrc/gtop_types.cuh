@@ -69,6 +69,8 @@ struct EvalScalars {
   double alpha, d0;       // distance penalty (:507-515)
   double inv_r;           // 1/r
   double alpha_over_r;    // alpha/r
+  double neg_log2e_over_r;  // -log2(e)/r      } exp(-(d-d0)/r) = 2^(d*neg_log2e_over_r + d0_log2e_over_r)
+  double d0_log2e_over_r;   // d0*log2(e)/r    }
   int skip_collision;     // |wc| < 1e-4 (:346)
 };
 
