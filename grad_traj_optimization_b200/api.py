@@ -161,6 +161,19 @@ class ProblemSet:
         check(lib().gtop_problems_create_from_paths(np_, m, _dp(w), C.byref(p), int(device), C.byref(h)))
         return cls(h, p, int(device))
 
+    @classmethod
+    def from_kino(cls, pos, vel, acc, time, params, device=0):
+        """Front-end hand-off (setKinoPath, grad_traj_optimizer.cpp:35-65): pos/vel/acc [np, m+1, 3], time [np, m]."""
+        t = _f64(time)
+        t = t.reshape(-1, t.shape[-1])
+        np_, m = t.shape
+        P, V, A = (_f64(a, (np_, m + 1, 3)) for a in (pos, vel, acc))
+        p = params if isinstance(params, GtopParams) else make_params(params)
+        h = C.c_void_p()
+        check(lib().gtop_problems_create_from_kino(np_, m, _dp(P), _dp(V), _dp(A), _dp(t), C.byref(p), int(device),
+                                                   C.byref(h)))
+        return cls(h, p, int(device))
+
     def close(self):
         if getattr(self, "h", None):
             lib().gtop_problems_destroy(self.h)

@@ -419,6 +419,27 @@ int gtop_problems_create_from_paths(int32_t np, int32_t m, const double* waypoin
   return finish_problems(p, out);
 }
 
+int gtop_problems_create_from_kino(int32_t np, int32_t m, const double* pos, const double* vel, const double* acc,
+                                   const double* time, const gtop_params* prm, int device, gtop_problems** out) {
+  REQUIRE(np >= 1 && m >= 2 && pos && vel && acc && time && out, "bad argument");
+  if (int rc = check_params(prm)) return rc;
+  REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  gtop_problems* p = new gtop_problems();
+  p->device = device, p->np = np, p->prm = *prm;
+  p->layout = make_layout(m, prm->samples_per_segment);
+  p->host.resize(np);
+  const size_t w = (size_t)(m + 1) * 3;
+  for (int i = 0; i < np; ++i) {
+    std::string err = setup_from_kino(m, pos + i * w, vel + i * w, acc + i * w, time + (size_t)i * m, *prm, p->host[i]);
+    if (!err.empty()) {
+      delete p;
+      return fail(GTOP_E_INVALID, "problem " + std::to_string(i) + ": " + err);
+    }
+  }
+  return finish_problems(p, out);
+}
+
 int gtop_problems_destroy(gtop_problems* p) {
   if (!p) return GTOP_OK;
   cudaSetDevice(p->device);

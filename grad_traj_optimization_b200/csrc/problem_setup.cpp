@@ -136,22 +136,14 @@ std::string setup_from_dense(int m, const double* seg_time, const double* L, con
   return "";
 }
 
-std::string setup_from_path(int m, const double* wp, const gtop_params& prm, ProblemHost& out) {
-  if (m < 2) return "need at least 2 segments";
-  if (prm.samples_per_segment < 1) return "samples_per_segment must be >= 1";
-  if (!(prm.mean_v > 0.0)) return "mean_v must be > 0";
-  out = ProblemHost();
-  out.m = m;
-  out.ns_cap = prm.samples_per_segment;
+// Shared tail of the native set-up: per-segment blocks, banded R, Df, x0, bounds, time table.
+// pos: (m+1) x 3 waypoint positions; vel/acc: (m+1) x 3 or nullptr (zeros).
+static std::string setup_common(int m, const double* pos, const double* vel, const double* acc, const gtop_params& prm,
+                                ProblemHost& out) {
   const int nd = 3 * m + 3, P = 3 * m - 3, n = 3 * P;
-  // time allocation (grad_traj_optimizer.cpp:73-81; init_time on the first segment only, H9)
-  out.seg_time.assign(m, 0.0);
-  for (int i = 0; i < m; ++i) {
-    const double dx = wp[3 * i] - wp[3 * i + 3], dy = wp[3 * i + 1] - wp[3 * i + 4], dz = wp[3 * i + 2] - wp[3 * i + 5];
-    const double len = std::sqrt(dx * dx + dy * dy + dz * dz);
-    out.seg_time[i] = (i == 0) ? len / prm.mean_v + prm.init_time : len / prm.mean_v;
-    if (!(out.seg_time[i] > 0.0)) return "zero-length segment (coincident waypoints)";
-  }
+  const double* wp = pos;
+  for (int i = 0; i < m; ++i)
+    if (!(out.seg_time[i] > 0.0)) return "non-positive segment time (coincident waypoints?)";
   out.Linv.assign((size_t)m * 36, 0.0);
   out.Mseg.assign((size_t)m * 36, 0.0);
   for (int s = 0; s < m; ++s) {
@@ -222,14 +214,45 @@ std::string setup_from_path(int m, const double* wp, const gtop_params& prm, Pro
     for (int i = 0; i < P; ++i) {
       const int w = i / 3 + 1, q = i % 3;
       const double c = wp[3 * w + a];
-      out.x0[a * P + i] = (q == 0) ? c : 0.0;
+      out.x0[a * P + i] = (q == 0) ? c : (q == 1 ? (vel ? vel[3 * w + a] : 0.0) : (acc ? acc[3 * w + a] : 0.0));
       const double half = q == 0 ? prm.bos : (q == 1 ? prm.vos : prm.aos);
-      out.lb[a * P + i] = (q == 0 ? c : 0.0) - half;
+      out.lb[a * P + i] = (q == 0 ? c : 0.0) - half;  // box centred on the path / on zero (:154-177)
       out.ub[a * P + i] = (q == 0 ? c : 0.0) + half;
     }
   out.has_path = true;
   build_time_table(out);
   return "";
+}
+
+std::string setup_from_path(int m, const double* wp, const gtop_params& prm, ProblemHost& out) {
+  if (m < 2) return "need at least 2 segments";
+  if (prm.samples_per_segment < 1) return "samples_per_segment must be >= 1";
+  if (!(prm.mean_v > 0.0)) return "mean_v must be > 0";
+  out = ProblemHost();
+  out.m = m;
+  out.ns_cap = prm.samples_per_segment;
+  // time allocation (grad_traj_optimizer.cpp:73-81; init_time on the first segment only, H9)
+  out.seg_time.assign(m, 0.0);
+  for (int i = 0; i < m; ++i) {
+    const double dx = wp[3 * i] - wp[3 * i + 3], dy = wp[3 * i + 1] - wp[3 * i + 4], dz = wp[3 * i + 2] - wp[3 * i + 5];
+    const double len = std::sqrt(dx * dx + dy * dy + dz * dz);
+    out.seg_time[i] = (i == 0) ? len / prm.mean_v + prm.init_time : len / prm.mean_v;
+  }
+  return setup_common(m, wp, nullptr, nullptr, prm, out);
+}
+
+// setKinoPath (grad_traj_optimizer.cpp:35-65) + PolyKinoGeneration (qp_generator.cpp:23-154): segment times
+// are given; x0 carries the front end's velocities / accelerations at the interior waypoints; Df keeps zero
+// start/end velocity and acceleration (startVel/startAcc are stale zero globals upstream — SURVEY H14).
+std::string setup_from_kino(int m, const double* pos, const double* vel, const double* acc, const double* time,
+                            const gtop_params& prm, ProblemHost& out) {
+  if (m < 2) return "need at least 2 segments";
+  if (prm.samples_per_segment < 1) return "samples_per_segment must be >= 1";
+  out = ProblemHost();
+  out.m = m;
+  out.ns_cap = prm.samples_per_segment;
+  out.seg_time.assign(time, time + m);
+  return setup_common(m, pos, vel, acc, prm, out);
 }
 
 void dense_L(const ProblemHost& p, double* L) {

@@ -40,6 +40,8 @@ inline int dense_col(int m, int wp, int q) { return wp == 0 ? q : (wp == m ? 3 +
 std::string setup_from_dense(int m, const double* seg_time, const double* L, const double* R, const double* Df_colmajor,
                              const gtop_params& prm, ProblemHost& out);
 std::string setup_from_path(int m, const double* waypoints /* (m+1) x 3 */, const gtop_params& prm, ProblemHost& out);
+std::string setup_from_kino(int m, const double* pos, const double* vel, const double* acc /* (m+1) x 3 each */,
+                            const double* time /* m */, const gtop_params& prm, ProblemHost& out);
 
 // sample-time table of one problem (dt, ns, tt), from seg_time and samples_per_segment
 void build_time_table(ProblemHost& p);

@@ -17,6 +17,7 @@
  *   gtop_problems_create_dense the members L, R, Df, segment_time left by setPath   src/grad_traj_optimizer.cpp:67-110
  *                              (TrajectoryGenerator::StackOptiDep/getInitialD       src/qp_generator.cpp:357-451)
  *   gtop_problems_create_from_paths  setPath itself (time allocation :73-81 + PolyQPGeneration/StackOptiDep/getInitialD)
+ *   gtop_problems_create_from_kino   setKinoPath                                   src/grad_traj_optimizer.cpp:35-65 (PolyKinoGeneration src/qp_generator.cpp:23-154)
  *   gtop_eval_batch_device / _host   GradTrajOptimizer::getCostAndGradient          src/grad_traj_optimizer.cpp:281-448, batched
  *   gtop_objective             GradTrajOptimizer::costFunc (NLopt callback)         src/grad_traj_optimizer.cpp:554-562,
  *                              registered by set_min_objective(costFunc, this)      src/grad_traj_optimizer.cpp:140
@@ -120,6 +121,12 @@ int gtop_problems_create_dense(int32_t num_problems, int32_t m, const double* se
  * mapping blocks, banded R, Df, x0 and bounds, built block-wise in O(m) (no dense (6m)^2 inverse). */
 int gtop_problems_create_from_paths(int32_t num_problems, int32_t m, const double* waypoints, const gtop_params* params,
                                     int device, gtop_problems** out);
+/* Front-end hand-off (setKinoPath, grad_traj_optimizer.cpp:35-65): positions / velocities / accelerations at
+ * the m+1 waypoints (num_problems x (m+1) x 3 each, row-major) and the segment times (num_problems x m) of a
+ * kinodynamic search (getKinoTrajMat).  x0 carries the interior velocities / accelerations. */
+int gtop_problems_create_from_kino(int32_t num_problems, int32_t m, const double* pos, const double* vel,
+                                   const double* acc, const double* time, const gtop_params* params, int device,
+                                   gtop_problems** out);
 int gtop_problems_destroy(gtop_problems* p);
 int gtop_problems_dims(const gtop_problems* p, int32_t* num_problems, int32_t* m, int32_t* n /* = 9(m-1) */);
 int gtop_problems_set_params(gtop_problems* p, const gtop_params* params); /* weights / penalty constants only */

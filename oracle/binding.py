@@ -282,9 +282,10 @@ class OracleOptimizer:
                                         int(nthreads), C.byref(oob))
         return cost, grad, int(oob.value), secs
 
-    def solve(self, step=2, maxeval=100, maxtime=0.0, xtol_abs=0.0, objective=None):
+    def solve(self, step=2, maxeval=100, maxtime=0.0, xtol_abs=0.0, objective=None, c_objective=None):
         """NLopt LD_MMA solve from the current Dp.  `objective(x, grad) -> float` (optional) replaces
-        the oracle objective (numpy views of NLopt's buffers)."""
+        the oracle objective (numpy views of NLopt's buffers); `c_objective=(fn_ptr, data_ptr)` does the
+        same with a native nlopt_func (e.g. the product's gtop_objective and its context)."""
         path = nlopt_path()
         if path is None:
             raise RuntimeError("vendored NLopt binary not available (oracle/_ref/libnlopt.so.0)")
@@ -301,8 +302,11 @@ class OracleOptimizer:
         x = np.empty(self.n)
         minf = C.c_double(0)
         nev = C.c_int(0)
+        fptr, fdata = (C.cast(cb, C.c_void_p), None) if cb else (None, None)
+        if c_objective is not None:
+            fptr, fdata = c_objective
         r = lib().gto_opt_solve(self.h, int(step), int(maxeval), float(maxtime), float(xtol_abs), path.encode(),
-                                C.cast(cb, C.c_void_p) if cb else None, None, _dp(x), C.byref(minf), C.byref(nev))
+                                fptr, fdata, _dp(x), C.byref(minf), C.byref(nev))
         if r <= -1000:
             raise RuntimeError("oracle solve failed: %d %s" % (r, lib().gto_last_error().decode()))
         return x, minf.value, r, nev.value

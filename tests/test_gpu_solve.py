@@ -1,0 +1,105 @@
+"""NLopt-converged trajectories: GPU objective vs CPU oracle objective through the SAME solver.
+
+The vendored NLopt 2.5.0 LD_MMA (oracle/_ref/libnlopt.so.0) drives (a) the oracle objective and (b) the
+product's gtop_objective callback from the same x0 and bounds with a maxeval stop (the reference's only
+stopping rule is wall clock — SURVEY H7).  Gate: trajectories sampled every 0.01 s differ by
+<= 1e-4 m at maxeval = 100; also the two-stage OPT_FIRST_STEP -> OPT_SECOND_STEP sequence with 50 + 50."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import oracle_map_from_cfg, oracle_problem
+from grad_traj_optimization_b200 import fixtures as fx
+from oracle import nlopt_path
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(nlopt_path() is None, reason="vendored NLopt binary not shipped (oracle/_ref/libnlopt.so.0)")]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sample_traj(coeff, seg_time, dt=0.01):
+    """Positions every `dt` s along the piecewise quintic (as polynomial_traj.hpp:69-78 upstream)."""
+    pts, t_end = [], float(np.sum(seg_time))
+    t = 0.0
+    bounds = np.concatenate([[0.0], np.cumsum(seg_time)])
+    while t <= t_end:
+        s = min(int(np.searchsorted(bounds, t, side="right")) - 1, len(seg_time) - 1)
+        tau = t - bounds[s]
+        pw = tau ** np.arange(6)
+        pts.append([coeff[s, 0:6] @ pw, coeff[s, 6:12] @ pw, coeff[s, 12:18] @ pw])
+        t += dt
+    return np.asarray(pts)
+
+
+def _gpu(cfg):
+    from grad_traj_optimization_b200 import api
+    gm = api.SdfMap(cfg["map_origin"], cfg["resolution"], cfg["map_size"])
+    gm.update(cfg["obstacles"])
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+    return api, gm, ps
+
+
+@pytest.mark.parametrize("name", ["text_input", "opti_node"])
+@pytest.mark.parametrize("maxeval", [40, 100])
+def test_single_stage_solve_trajectory_parity(gtop_lib, name, maxeval):
+    cfg = fx.load_cfg(name)
+    om = oracle_map_from_cfg(cfg)
+    ref = oracle_problem(cfg, om, cfg["waypoints"])
+    x_ref, f_ref, _, nev_ref = ref.solve(step=2, maxeval=maxeval)
+    api, gm, ps = _gpu(cfg)
+    obj = api.Objective(gm, ps, 0, step=2)
+    drv = oracle_problem(cfg, om, cfg["waypoints"])  # same driver / bounds / x0, GPU objective plugged in
+    x_gpu, f_gpu, _, _ = drv.solve(step=2, maxeval=maxeval, c_objective=obj.c_callback)
+    assert obj.evals == nev_ref == maxeval
+    T = ref.seg_time()
+    dev = np.linalg.norm(sample_traj(ref.coeff_from_x(x_ref), T) - sample_traj(ps.coeff_from_x(x_gpu), T), axis=1).max()
+    assert dev <= 1e-4, "trajectory deviation %.3e m" % dev
+    assert abs(f_gpu - f_ref) <= 1e-6 * abs(f_ref)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "fixtures_solve.npz"))
+    dev_g = np.linalg.norm(sample_traj(gold["%s_coeff_maxeval%d" % (name, maxeval)], T) -
+                           sample_traj(ps.coeff_from_x(x_gpu), T), axis=1).max()
+    assert dev_g <= 1e-4
+
+
+def test_two_stage_sequence_parity(gtop_lib):
+    """example_text_input.cpp:121-127: OPT_FIRST_STEP then OPT_SECOND_STEP, Dp carried between the stages."""
+    cfg = fx.load_cfg("text_input")
+    om = oracle_map_from_cfg(cfg)
+    ref = oracle_problem(cfg, om, cfg["waypoints"])
+    ref.solve(step=1, maxeval=50)
+    x_ref, _, _, _ = ref.solve(step=2, maxeval=50)
+    api, gm, ps = _gpu(cfg)
+    obj = api.Objective(gm, ps, 0, step=1)
+    drv = oracle_problem(cfg, om, cfg["waypoints"])
+    drv.solve(step=1, maxeval=50, c_objective=obj.c_callback)
+    obj.set_step(2)
+    x_gpu, _, _, _ = drv.solve(step=2, maxeval=50, c_objective=obj.c_callback)
+    T = ref.seg_time()
+    dev = np.linalg.norm(sample_traj(ref.coeff_from_x(x_ref), T) - sample_traj(ps.coeff_from_x(x_gpu), T), axis=1).max()
+    assert dev <= 1e-4, "trajectory deviation %.3e m" % dev
+
+
+@pytest.mark.parametrize("name", ["text_input", "opti_node"])
+def test_cpp_harness_end_to_end(gtop_lib, name, tmp_path):
+    """The ROS-free C++ harness (GradTrajOptimizer mirror over the C ABI): fixture file -> GPU EDT -> setPath ->
+    NLopt solve with the GPU objective; converged coefficients vs the oracle's golden solve."""
+    exe = os.path.join(ROOT, "grad_traj_optimization_b200", "gtop_harness")
+    assert os.path.exists(exe), "gtop_harness is not built (run __graft_entry__.build())"
+    dump = tmp_path / "coeff.txt"
+    r = subprocess.run([exe, os.path.join(ROOT, "configs", name + ".cfg"), "--maxeval", "100", "--steps", "2", "--nlopt",
+                        nlopt_path(), "--dump", str(dump)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    gold_eval = np.load(os.path.join(ROOT, "tests", "golden", "fixtures_eval.npz"))
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "fixtures_solve.npz"))
+    for step in (1, 2):
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("x0 step %d" % step)][0]
+        cost = float(line.split("cost")[1].split()[0])
+        ref = gold_eval["%s_cost_step%d" % (name, step)][0]  # start 0 of the golden batch is x0
+        assert abs(cost - ref) <= 1e-9 * abs(ref)
+    coeff = np.loadtxt(dump)
+    T = gold_eval[name + "_seg_time"]
+    dev = np.linalg.norm(sample_traj(gold[name + "_coeff_maxeval100"], T) - sample_traj(coeff, T), axis=1).max()
+    assert dev <= 1e-4, "trajectory deviation %.3e m" % dev
