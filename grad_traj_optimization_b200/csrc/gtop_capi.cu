@@ -26,7 +26,7 @@ cudaError_t launch_set_occupancy(const SdfView& S, uint8_t* occ, const double* p
 cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t* boxes_dev, int64_t n,
                              cudaStream_t st);
 cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
-                       cudaStream_t st, cudaEvent_t* ev);
+                       bool fresh, cudaStream_t st, cudaEvent_t* ev);
 cudaError_t launch_query(const SdfView& S, const double* pos_dev, int64_t n, double* dist_dev, double* grad_dev,
                          unsigned long long* oob_dev, cudaStream_t st);
 }  // namespace gtop
@@ -64,6 +64,7 @@ struct gtop_sdf {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[4] = {0, 0, 0, 0};
+  bool dist_fresh = false;  // distance buffer is 10000 everywhere (just created / reset)
 };
 
 struct gtop_problems {
@@ -256,7 +257,9 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
     if (e == cudaSuccess) e = cudaMalloc(&s->d2, sizeof(int32_t) * s->nvox);
     if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("edt scratch: ") + cudaGetErrorString(e));
   }
-  CU(launch_edt(s->occ, s->d1, s->d2, s->dist, s->view.nx, s->view.ny, s->view.nz, s->view.res, s->stream, s->ev));
+  CU(launch_edt(s->occ, s->d1, s->d2, s->dist, s->view.nx, s->view.ny, s->view.nz, s->view.res, s->dist_fresh, s->stream,
+                s->ev));
+  s->dist_fresh = false;
   CU(launch_build_pairs(s->dist, s->pair, s->nvox, s->view.nz, s->stream));
   g_launches += 4;
   CU(cudaStreamSynchronize(s->stream));

@@ -124,35 +124,51 @@ k_edt_z(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t ncol
 // < 32768 long).  F(x,i) = (x-i)^2 + g(i).
 template <int MAXN, bool FINAL>
 __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int64_t gstride, int n,
-                                             int32_t* __restrict__ out_i, double* __restrict__ out_d, double res) {
+                                             int32_t* __restrict__ out_i, double* __restrict__ out_d, double res,
+                                             bool fresh) {
   short s[MAXN];  // sites
   short t[MAXN];  // t[q]: first x at which site s[q] is the minimiser
   int gs[MAXN];   // g(s[q]) cached next to the stack (avoids a dependent strided re-load)
   int q = -1;
-  for (int u = 0; u < n; ++u) {
-    const int gu = g[(int64_t)u * gstride];
-    if (gu >= kInf) continue;  // an infinite parabola never wins
-    // pop while the new parabola is below the top one at the top's start
-    while (q >= 0) {
-      const int x = t[q], dq = x - s[q], du = x - u;
-      if ((long long)dq * dq + gs[q] > (long long)du * du + gu) --q;
-      else break;
+  // The row loads do not depend on the stack: fetch them kPF elements ahead so that several strided
+  // (and, in the x pass, TLB-missing) loads are in flight while the envelope logic runs.
+  constexpr int kPF = 8;
+  int gbuf[kPF];
+#pragma unroll
+  for (int k = 0; k < kPF; ++k) gbuf[k] = (k < n) ? g[(int64_t)k * gstride] : kInf;
+  for (int u0 = 0; u0 < n; u0 += kPF) {
+    int gcur[kPF];
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      gcur[k] = gbuf[k];
+      const int un = u0 + kPF + k;
+      gbuf[k] = (un < n) ? g[(int64_t)un * gstride] : kInf;
     }
-    if (q < 0) {
-      q = 0, s[0] = (short)u, t[0] = 0, gs[0] = gu;
-    } else {
-      // Sep(i,u) = floor((u^2 - i^2 + g(u) - g(i)) / (2(u-i))): last x where site i still wins
-      const int i = s[q];
-      const long long num = (long long)u * u - (long long)i * i + (long long)gu - (long long)gs[q];
-      const int w = 1 + (int)(num / (2LL * (u - i)));
-      if (w < n) ++q, s[q] = (short)u, t[q] = (short)w, gs[q] = gu;
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      const int u = u0 + k, gu = gcur[k];
+      if (gu >= kInf) continue;  // an infinite parabola never wins (also pads past the row end)
+      // pop while the new parabola is below the top one at the top's start
+      while (q >= 0) {
+        const int x = t[q], dq = x - s[q], du = x - u;
+        if ((long long)dq * dq + gs[q] > (long long)du * du + gu) --q;
+        else break;
+      }
+      if (q < 0) {
+        q = 0, s[0] = (short)u, t[0] = 0, gs[0] = gu;
+      } else {
+        // Sep(i,u) = floor((u^2 - i^2 + g(u) - g(i)) / (2(u-i))): last x where site i still wins
+        const int i = s[q];
+        const long long num = (long long)u * u - (long long)i * i + (long long)gu - (long long)gs[q];
+        const int w = 1 + (int)(num / (2LL * (u - i)));
+        if (w < n) ++q, s[q] = (short)u, t[q] = (short)w, gs[q] = gu;
+      }
     }
   }
-  if (q < 0) {  // whole row infinite
+  if (q < 0) {  // whole row infinite: res*sqrt(DBL_MAX) upstream, never below the old value (<= 10000)
     for (int u = 0; u < n; ++u) {
       if (FINAL) {
-        double* o = out_d + (int64_t)u * gstride;
-        *o = fmin(1.0e300, *o);  // res*sqrt(DBL_MAX) in the reference: never below the old value
+        if (fresh) out_d[(int64_t)u * gstride] = 10000.0;
       } else {
         out_i[(int64_t)u * gstride] = kInf;
       }
@@ -165,7 +181,9 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
     const int val = d * d + gs[q];
     if (FINAL) {
       double* o = out_d + (int64_t)u * gstride;
-      *o = fmin(res * sqrt((double)val), *o);  // sdf_map.cpp:356-360
+      // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360); after resetBuffer old is 10000 everywhere,
+      // so the read of the old value is skipped
+      *o = fmin(res * sqrt((double)val), fresh ? 10000.0 : *o);
     } else {
       out_i[(int64_t)u * gstride] = val;
     }
@@ -180,22 +198,22 @@ k_edt_y(const int32_t* __restrict__ in, int32_t* __restrict__ out, int nx, int n
   if (r >= (int64_t)nx * nz) return;
   const int x = (int)(r / nz), z = (int)(r % nz);
   const int64_t base = (int64_t)x * ny * nz + z;
-  envelope_row<MAXN, false>(in + base, nz, ny, out + base, nullptr, 0.0);
+  envelope_row<MAXN, false>(in + base, nz, ny, out + base, nullptr, 0.0, false);
 }
 
 // pass x: row = (y,z); element x at (x*ny*nz + (y*nz + z)); writes the fp64 distance buffer
 template <int MAXN>
 __global__ void __launch_bounds__(128)
-k_edt_x(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, int ny, int nz, double res) {
+k_edt_x(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, int ny, int nz, double res, bool fresh) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t plane = (int64_t)ny * nz;
   if (r >= plane) return;
-  envelope_row<MAXN, true>(in + r, plane, nx, nullptr, dist + r, res);
+  envelope_row<MAXN, true>(in + r, plane, nx, nullptr, dist + r, res, fresh);
 }
 
 template <int MAXN>
 static cudaError_t launch_yx(const int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
-                             cudaStream_t st, cudaEvent_t ev_mid) {
+                             bool fresh, cudaStream_t st, cudaEvent_t ev_mid) {
   const int threads = 128;
   {
     const int64_t rows = (int64_t)nx * nz;
@@ -204,7 +222,7 @@ static cudaError_t launch_yx(const int32_t* d1, int32_t* d2, double* dist, int n
   if (ev_mid) cudaEventRecord(ev_mid, st);
   {
     const int64_t rows = (int64_t)ny * nz;
-    k_edt_x<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d2, dist, nx, ny, nz, res);
+    k_edt_x<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d2, dist, nx, ny, nz, res, fresh);
   }
   return cudaGetLastError();
 }
@@ -235,7 +253,7 @@ cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t
 
 // full EDT: occ -> d1 (z) -> d2 (y) -> dist (x).  ev[0..3] (nullable) bracket the three passes.
 cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
-                       cudaStream_t st, cudaEvent_t* ev) {
+                       bool fresh, cudaStream_t st, cudaEvent_t* ev) {
   const int64_t ncols = (int64_t)nx * ny;
   if (ev) cudaEventRecord(ev[0], st);
   {
@@ -248,13 +266,15 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
   const int maxn = nx > ny ? nx : ny;
   cudaError_t e;
   if (maxn <= 256)
-    e = launch_yx<256>(d1, d2, dist, nx, ny, nz, res, st, ev ? ev[2] : nullptr);
+    e = launch_yx<256>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
   else if (maxn <= 1024)
-    e = launch_yx<1024>(d1, d2, dist, nx, ny, nz, res, st, ev ? ev[2] : nullptr);
+    e = launch_yx<1024>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
+  else if (maxn <= 2048)
+    e = launch_yx<2048>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
   else if (maxn <= 4096)
-    e = launch_yx<4096>(d1, d2, dist, nx, ny, nz, res, st, ev ? ev[2] : nullptr);
+    e = launch_yx<4096>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
   else if (maxn <= 16384)
-    e = launch_yx<16384>(d1, d2, dist, nx, ny, nz, res, st, ev ? ev[2] : nullptr);
+    e = launch_yx<16384>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
   else
     return cudaErrorInvalidValue;
   if (ev) cudaEventRecord(ev[3], st);

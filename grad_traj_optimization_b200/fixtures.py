@@ -217,3 +217,72 @@ def straight_line_x0(waypoints, bos=3.0, vos=8.0, aos=10.0):
         half[a * P + 1:(a + 1) * P:3] = vos
         half[a * P + 2:(a + 1) * P:3] = aos
     return x0, x0 - half, x0 + half
+
+
+# ------------------------------------------------------------------------------------------------
+# Map B (BASELINE configs[3]): 100x100x20 m @0.05 m = 2000x2000x400 voxels, 3,000 box pillars
+# ------------------------------------------------------------------------------------------------
+MAP_B = dict(map_size=np.array([100.0, 100.0, 20.0]), map_origin=np.array([-50.0, -50.0, 0.0]), resolution=0.05)
+
+
+def box_pillars(n_pillars, seed, grid, half_width_vox=5, height_vox=(40, 300), margin_vox=100):
+    """Voxel boxes [x0,y0,z0,x1,y1,z1] (inclusive) of `n_pillars` square pillars standing on the floor:
+    (2*half+1)^2 footprint, centre uniform inside the grid minus a margin, height uniform in `height_vox`."""
+    rng = Rng(seed)
+    u = rng.uniform((n_pillars, 3))
+    cx = (margin_vox + u[:, 0] * (grid[0] - 2 * margin_vox)).astype(np.int64)
+    cy = (margin_vox + u[:, 1] * (grid[1] - 2 * margin_vox)).astype(np.int64)
+    hz = (height_vox[0] + u[:, 2] * (height_vox[1] - height_vox[0])).astype(np.int64)
+    b = np.stack([cx - half_width_vox, cy - half_width_vox, np.zeros_like(cx), cx + half_width_vox, cy + half_width_vox,
+                  np.minimum(hz, grid[2] - 1)], axis=1)
+    return b.astype(np.int32)
+
+
+def boxes_exact_distance(boxes, vox, resolution):
+    """Exact unsigned EDT value at voxel indices `vox` [N,3] for a map whose occupied set is the union of
+    the voxel boxes: min over boxes of the integer squared distance to the box, then res*sqrt (bit-exact
+    with updateESDF3d, sdf_map.cpp:356-360)."""
+    vox = np.asarray(vox, dtype=np.int64)
+    best = np.full(vox.shape[0], np.iinfo(np.int64).max)
+    lo, hi = boxes[:, 0:3].astype(np.int64), boxes[:, 3:6].astype(np.int64)
+    for i in range(boxes.shape[0]):
+        d = np.maximum(np.maximum(lo[i] - vox, vox - hi[i]), 0)
+        best = np.minimum(best, (d * d).sum(axis=1))
+    return np.minimum(resolution * np.sqrt(best.astype(np.float64)), 10000.0)
+
+
+def boxes_clearance_fn(boxes, origin, resolution, clearance):
+    """is_free(p) for waypoint placement on a box map: horizontal distance to every pillar footprint
+    >= clearance (pillars treated as infinitely tall)."""
+    lo = origin[:2] + boxes[:, 0:2] * resolution
+    hi = origin[:2] + (boxes[:, 3:5] + 1) * resolution
+
+    def is_free(p):
+        d = np.maximum(np.maximum(lo - p[:2], p[:2] - hi), 0.0)
+        return bool(np.min((d * d).sum(axis=1)) >= clearance * clearance)
+
+    return is_free
+
+
+def random_waypoints_free(problem_id, m, is_free, xy_limit, start_x, start_y_span=6.0, step_len=(1.2, 2.5),
+                          jitter_deg=40.0, z_mid=2.0, z_amp=0.5):
+    """`random_waypoints` with a caller-supplied clearance predicate (used for the large box map)."""
+    rng = Rng(1000 + problem_id)
+    for _ in range(400):
+        p = np.array([start_x, -start_y_span + 2 * start_y_span * rng.uniform(), z_mid + z_amp * (2.0 * rng.uniform() - 1.0)])
+        if is_free(p):
+            break
+    pts, heading = [p], 0.0
+    while len(pts) < m + 1:
+        for attempt in range(400):
+            spread = np.deg2rad(jitter_deg) if attempt < 40 else np.pi
+            h = heading + spread * (2.0 * rng.uniform() - 1.0)
+            ln = step_len[0] + (step_len[1] - step_len[0]) * rng.uniform()
+            q = np.array([pts[-1][0] + ln * np.cos(h), pts[-1][1] + ln * np.sin(h), z_mid + z_amp * (2.0 * rng.uniform() - 1.0)])
+            if abs(q[0]) <= xy_limit and abs(q[1]) <= xy_limit and is_free(q):
+                break
+        else:
+            raise RuntimeError("random_waypoints_free: could not place waypoint %d of problem %d" % (len(pts), problem_id))
+        heading = h
+        pts.append(q)
+    return np.asarray(pts)
