@@ -1,0 +1,149 @@
+// eval_common.cuh — device helpers shared by the two cost+gradient kernels (eval_kernel.cu: one
+// quarter-warp per trajectory, any batch; eval_mma_kernel.cu: multi-start batches on FP64 DMMA).
+//
+// Rounding discipline: everything that feeds the float truncation of position /
+// velocity (grad_traj_optimizer.cpp:457-485) and the voxel index / diff arithmetic
+// (sdf_map.cpp:201-209) is evaluated in the reference's operation order with __dmul_rn/__dadd_rn
+// (no FMA contraction), so cell selection and the fp32 round trip are bit-identical to the CPU
+// path.  Everything downstream is smooth and free to fuse / reorder.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gtop_types.cuh"
+
+namespace gtop {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- branch-free FP64 helpers for the smooth part of the sample pass (no special-case paths: the
+// library sqrt/div/exp carry slow-path branches that split the sample body into basic blocks and
+// keep the scheduler from overlapping the gather latency with arithmetic) ---------------------------
+__device__ __forceinline__ double rcp_seed(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));  // MUFU.RCP64H, ~20 good bits
+  return r;
+}
+__device__ __forceinline__ double rsqrt_seed(double a) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));  // MUFU.RSQ64H, ~20 good bits
+  return r;
+}
+// sqrt(a) for a in the normal range (a >= 1e-300): one coupled Newton (Goldschmidt) step from the
+// 20-bit seed (-> ~2^-40) and one residual correction (-> < 1 ulp)
+__device__ __forceinline__ double sqrt_pos(double a) {
+  const double y = rsqrt_seed(a);
+  double t = a * y, h = 0.5 * y;
+  const double r = fma(-t, h, 0.5);
+  t = fma(t, r, t), h = fma(h, r, h);
+  return fma(fma(-t, t, a), h, t);
+}
+// 1/a for a in the normal range: seed (2^-20), cubic step e + e^2 (-> 2^-60)
+__device__ __forceinline__ double rcp_pos(double a) {
+  const double y = rcp_seed(a);
+  const double e = fma(-a, y, 1.0);
+  return fma(y, fma(e, e, e), y);
+}
+
+// 2^y for y in [-1000, 1000]: y = k + j/16 + r, |r| <= 1/32; 2^y = 2^k * T[j] * 2^r with a degree-6
+// Taylor polynomial for 2^r (truncation (ln2/32)^7/7! = 4e-16).  T = 2^(j/16), 16 doubles = one
+// conflict-free shared-memory wavefront per warp.
+constexpr int kExpTab = 16;
+__device__ __forceinline__ void exp2_tab_init(double* T, int tid, int nthreads) {
+  for (int i = tid; i < kExpTab; i += nthreads) T[i] = exp2((double)i * (1.0 / kExpTab));
+}
+__device__ __forceinline__ double exp2_tab(double y, const double* __restrict__ T) {
+  const double kMagic = 422212465065984.0;  // 1.5 * 2^48: ulp = 1/16
+  const double z = y + kMagic;
+  const int N = __double2loint(z);          // round(y*16)
+  const double r = y - (z - kMagic);
+  double p = 1.5403530393381609e-4;           // ln2^6/6!
+  p = fma(p, r, 1.3333558146428443e-3);       // ln2^5/5!
+  p = fma(p, r, 9.6181291076284772e-3);       // ln2^4/4!
+  p = fma(p, r, 5.5504108664821580e-2);       // ln2^3/3!
+  p = fma(p, r, 2.4022650695910071e-1);       // ln2^2/2!
+  p = fma(p, r, 6.9314718055994531e-1);       // ln2
+  const double tj = T[N & (kExpTab - 1)];
+  const double m = fma(tj * r, p, tj);        // T[j] * (1 + r*p)
+  return __hiloint2double(__double2hiint(m) + ((N >> 4) << 20), __double2loint(m));
+}
+
+__device__ __forceinline__ double f32_round_trip(double x) { return (double)__double2float_rn(x); }
+
+// ---- 256-bit gather of one xy-quad ----------------------------------------------------------------
+struct __align__(32) Quad {
+  double v00, v01, v10, v11;  // (x0,y0) (x0,y1) (x1,y0) (x1,y1) at one height
+};
+__device__ __forceinline__ Quad ldg_quad(const void* p) {
+  Quad q;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q.v00), "=d"(q.v01), "=d"(q.v10), "=d"(q.v11) : "l"(p));
+  return q;
+}
+
+// SDFMap::getDistWithGradTrilinear (sdf_map.cpp:185-242), split in two so that the caller can put
+// independent arithmetic between the gathers and their use:
+//   sdf_gather  : in-map test, cell index / diff (reference op order, unfused), 2 x LDG.256
+//   sdf_finish  : trilinear value and gradient; out of map -> dist=-1, grad=0 (H3), branch-free
+// The gradient is returned WITHOUT the 1/resolution factor (folded into the caller's constants).
+// Interpolation is evaluated as nested lerps a + d*(b-a): the corner differences are shared between
+// the value and the gradient; it differs from the reference's (1-d)*a + d*b form only by rounding.
+//
+// Clamped corners (getDistance(Vector3i) :166-174).  Inside the map idx >= -1 on every axis.  The
+// quad element of voxel (x,y) already carries the upper clamp (x+ = min(x+1,nx-1)); for idx = -1
+// both corners are voxel 0, which the quad of voxel 0 does not provide — `xlow`/`ylow` then evaluate
+// the cell at diff = 0 (value of corner 0) and zero that gradient component, which is what two equal
+// corners give.  Along z the two quads are addressed separately (z0, z1 clamped like the reference).
+struct SdfCell {
+  Quad q0, q1;  // heights z0, z1
+  double dx, dy, dz;
+  bool in_map, xlow, ylow;
+};
+
+__device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double py, double pz, float fx32, float fy32,
+                                           float fz32, SdfCell& c) {
+  // isInMap (:55-69) on the float images of the bounds: exact for float-valued positions
+  c.in_map = !(fx32 < S.lofx || fy32 < S.lofy || fz32 < S.lofz || fx32 > S.hifx || fy32 > S.hify || fz32 > S.hifz);
+  // pos_m = pos - 0.5*res; idx = floor((pos_m - origin)*res_inv)           (:201-204, :71-74)
+  const double fx = floor(__dmul_rn(__dsub_rn(__dsub_rn(px, S.half_res), S.ox), S.res_inv));
+  const double fy = floor(__dmul_rn(__dsub_rn(__dsub_rn(py, S.half_res), S.oy), S.res_inv));
+  const double fz = floor(__dmul_rn(__dsub_rn(__dsub_rn(pz, S.half_res), S.oz), S.res_inv));
+  // idx_pos = (idx + 0.5)*res + origin; diff = (pos - idx_pos)*res_inv     (:76-78, :209)
+  const double dx = __dmul_rn(__dsub_rn(px, __dadd_rn(__dmul_rn(__dadd_rn(fx, 0.5), S.res), S.ox)), S.res_inv);
+  const double dy = __dmul_rn(__dsub_rn(py, __dadd_rn(__dmul_rn(__dadd_rn(fy, 0.5), S.res), S.oy)), S.res_inv);
+  c.dz = __dmul_rn(__dsub_rn(pz, __dadd_rn(__dmul_rn(__dadd_rn(fz, 0.5), S.res), S.oz)), S.res_inv);
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  c.xlow = ix < 0, c.ylow = iy < 0;
+  c.dx = c.xlow ? 0.0 : dx;
+  c.dy = c.ylow ? 0.0 : dy;
+  // the clamps also keep the loads of an out-of-map sample inside the buffer: no branch needed
+  const int x0 = max(min(ix, S.nx - 1), 0), y0 = max(min(iy, S.ny - 1), 0);
+  const int z0 = max(min(iz, S.nz - 1), 0), z1 = max(min(iz + 1, S.nz - 1), 0);
+  const int e0 = ((((x0 >> 1) * S.nyh + (y0 >> 1)) * S.nz + z0) << 2) + ((x0 & 1) << 1) + (y0 & 1);
+  const char* p = (const char*)S.quad + (size_t)(unsigned)e0 * 32u;
+  c.q0 = ldg_quad(p);
+  c.q1 = ldg_quad(p + (z1 - z0) * 128);
+}
+
+// returns dist and the three gradient components (unscaled by 1/res); xlow/ylow/out-of-map handled
+__device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, double& gx, double& gy, double& gz) {
+  // x-lerps; the x-differences feed grad x
+  const double e00 = c.q0.v10 - c.q0.v00, e10 = c.q0.v11 - c.q0.v01;  // (y0,z0), (y1,z0)
+  const double e01 = c.q1.v10 - c.q1.v00, e11 = c.q1.v11 - c.q1.v01;  // (y0,z1), (y1,z1)
+  const double v00 = fma(c.dx, e00, c.q0.v00), v10 = fma(c.dx, e10, c.q0.v01);
+  const double v01 = fma(c.dx, e01, c.q1.v00), v11 = fma(c.dx, e11, c.q1.v01);
+  // y-lerps; y-differences feed grad y
+  const double f0 = v10 - v00, f1 = v11 - v01;
+  const double v0 = fma(c.dy, f0, v00), v1 = fma(c.dy, f1, v01);
+  const double h = v1 - v0;
+  const double d = fma(c.dz, h, v0);                      // :229
+  const double y = fma(c.dz, f1 - f0, f0);                // :232-233
+  const double ex0 = fma(c.dy, e10 - e00, e00), ex1 = fma(c.dy, e11 - e01, e01);
+  const double x = fma(c.dz, ex1 - ex0, ex0);             // :234-239
+  dist = c.in_map ? d : -1.0;                             // :187, H3
+  gx = (c.in_map && !c.xlow) ? x : 0.0;
+  gy = (c.in_map && !c.ylow) ? y : 0.0;
+  gz = c.in_map ? h : 0.0;                                // :231
+}
+
+}  // namespace gtop

@@ -7,11 +7,14 @@
 //       with SDFMap::getDistWithGradTrilinear (src/sdf_map.cpp:185-242) gathers from HBM/L2
 //   (c) coefficient map c = L d (getCoefficientFromDerivative :253-279) in per-segment 6x6 blocks
 //
+// This is the GENERAL kernel (every trajectory may belong to a different problem); multi-start batches
+// whose groups of 8 consecutive trajectories share a problem go to k_eval_mma (eval_mma_kernel.cu).
+//
 // Work decomposition (v4): a QUARTER-WARP (8 lanes) PER TRAJECTORY, four trajectories per warp
 // walking their segments in lock-step; there is no block-level barrier anywhere.  Inside a segment
 // lane j of the quarter takes samples j, j+8, j+16, ... (4 per lane at N_s = 30), so
-//   * the 8 lanes of a quarter gather from 8 consecutive samples (~0.5 m of path: 3-4 128-B lines
-//     of the z-fastest grid per 128-bit load instruction),
+//   * the 8 lanes of a quarter gather from 8 consecutive samples (~0.5 m of path: a few 128-B lines
+//     of the patch-ordered quad copy of the grid per 256-bit load instruction),
 //   * every lane has several independent sample iterations in flight (latency hiding by ILP; the
 //     kernel needs ~128 registers, i.e. 16 warps/SM),
 //   * the per-segment serial steps — coefficient staging, the cross-lane reduction of the 3x6
@@ -29,7 +32,10 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 
+#include "eval_common.cuh"
 #include "gtop_types.cuh"
 
 namespace gtop {
@@ -39,121 +45,6 @@ namespace gtop {
 #endif
 constexpr int kMaxWarpsPerCta = 4;
 constexpr int kTrajPerWarp = 4;  // quarter-warps
-constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ double f32_round_trip(double x) { return (double)__double2float_rn(x); }
-
-// ---- branch-free FP64 helpers for the smooth part of the sample pass (no special-case paths: the
-// library sqrt/div/exp carry slow-path branches that split the sample body into basic blocks and
-// keep the scheduler from overlapping the gather latency with arithmetic) ---------------------------
-__device__ __forceinline__ double rcp_seed(double a) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));  // MUFU.RCP64H, ~20 good bits
-  return r;
-}
-__device__ __forceinline__ double rsqrt_seed(double a) {
-  double r;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));  // MUFU.RSQ64H, ~20 good bits
-  return r;
-}
-// sqrt(a) for a in the normal range (a >= 1e-300): coupled Newton (Goldschmidt) + one residual step
-__device__ __forceinline__ double sqrt_pos(double a) {
-  const double y = rsqrt_seed(a);
-  double t = a * y, h = 0.5 * y;
-  double r = fma(-t, h, 0.5);
-  t = fma(t, r, t), h = fma(h, r, h);
-  r = fma(-t, h, 0.5);
-  t = fma(t, r, t), h = fma(h, r, h);
-  return fma(fma(-t, t, a), h, t);
-}
-// 1/a for a in the normal range
-__device__ __forceinline__ double rcp_pos(double a) {
-  double y = rcp_seed(a);
-  double e = fma(-a, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-a, y, 1.0);
-  return fma(y, e, y);
-}
-// 2^y for y in [-1000, 64]: y = k + j/64 + r, |r| <= 1/128;  2^y = 2^k * T[j] * 2^r with a degree-5
-// polynomial for 2^r (truncation 3.5e-17).  T = 2^(j/64) lives in shared memory.
-__device__ __forceinline__ double exp2_tab(double y, const double* __restrict__ T) {
-  const double kMagic = 105553116266496.0;  // 1.5 * 2^46: ulp = 1/64
-  const double z = y + kMagic;
-  const int N = __double2loint(z);            // round(y*64)
-  const double r = y - (z - kMagic);
-  double p = 1.3333558146428443e-3;           // ln2^5/5!
-  p = fma(p, r, 9.6181291076284772e-3);       // ln2^4/4!
-  p = fma(p, r, 5.5504108664821580e-2);       // ln2^3/3!
-  p = fma(p, r, 2.4022650695910071e-1);       // ln2^2/2!
-  p = fma(p, r, 6.9314718055994531e-1);       // ln2
-  const double tj = T[N & 63];
-  const double m = fma(tj * r, p, tj);        // T[j] * (1 + r*p)
-  return __hiloint2double(__double2hiint(m) + ((N >> 6) << 20), __double2loint(m));
-}
-
-// SDFMap::getDistWithGradTrilinear (sdf_map.cpp:185-242), split in two so that the caller can put
-// independent arithmetic between the 128-bit gathers and their use:
-//   sdf_gather  : in-map test, cell index / diff (reference op order, unfused), 4 x LDG.128
-//   sdf_finish  : trilinear value and gradient; out of map -> dist=-1, grad=0 (H3), branch-free
-// The gradient is returned WITHOUT the 1/resolution factor (folded into the caller's constants).
-// Interpolation is evaluated as nested lerps a + d*(b-a): the corner differences are shared between
-// the value and the gradient (25 FP64 ops instead of 46); it differs from the reference's
-// (1-d)*a + d*b form only by rounding (~1e-16 relative).
-struct SdfCell {
-  double2 q00, q01, q10, q11;  // (z, z+1) pairs of the four (x,y) columns
-  double dx, dy, dz;
-  bool in_map, zlow;
-};
-
-__device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double py, double pz, SdfCell& c) {
-  c.in_map = !(px < S.lox || py < S.loy || pz < S.loz || px > S.hix || py > S.hiy || pz > S.hiz);  // :55-69
-  // pos_m = pos - 0.5*res; idx = floor((pos_m - origin)*res_inv)           (:201-204, :71-74)
-  const double fx = floor(__dmul_rn(__dsub_rn(__dsub_rn(px, S.half_res), S.ox), S.res_inv));
-  const double fy = floor(__dmul_rn(__dsub_rn(__dsub_rn(py, S.half_res), S.oy), S.res_inv));
-  const double fz = floor(__dmul_rn(__dsub_rn(__dsub_rn(pz, S.half_res), S.oz), S.res_inv));
-  // idx_pos = (idx + 0.5)*res + origin; diff = (pos - idx_pos)*res_inv     (:76-78, :209)
-  c.dx = __dmul_rn(__dsub_rn(px, __dadd_rn(__dmul_rn(__dadd_rn(fx, 0.5), S.res), S.ox)), S.res_inv);
-  c.dy = __dmul_rn(__dsub_rn(py, __dadd_rn(__dmul_rn(__dadd_rn(fy, 0.5), S.res), S.oy)), S.res_inv);
-  c.dz = __dmul_rn(__dsub_rn(pz, __dadd_rn(__dmul_rn(__dadd_rn(fz, 0.5), S.res), S.oz)), S.res_inv);
-  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-  // clamped corner indices (getDistance(Vector3i) :166-174); the clamps also keep the loads of an
-  // out-of-map sample inside the buffer, so no branch is needed around the gather
-  const int x0 = max(min(ix, S.nx - 1), 0), x1 = max(min(ix + 1, S.nx - 1), 0);
-  const int y0 = max(min(iy, S.ny - 1), 0), y1 = max(min(iy + 1, S.ny - 1), 0);
-  // z-corners: one aligned 128-bit load per (x,y) column from the z-pair copy, pair[z] =
-  // (D[z], D[min(z+1,nz-1)]).  clamp(iz)/clamp(iz+1) differ from (zc, zc+1) only for iz = -1
-  // (both corners are D[0]); iz <= nz-1 always holds inside the map.
-  const int zc = max(min(iz, S.nz - 1), 0);
-  c.zlow = iz < 0;
-  const int syz = S.ny * S.nz;
-  const double2* __restrict__ D = S.pair + zc;
-  const int ox0 = x0 * syz, ox1 = x1 * syz, oy0 = y0 * S.nz, oy1 = y1 * S.nz;  // nvox < 2^31 (host check)
-  c.q00 = __ldg(D + ox0 + oy0), c.q01 = __ldg(D + ox0 + oy1);
-  c.q10 = __ldg(D + ox1 + oy0), c.q11 = __ldg(D + ox1 + oy1);
-}
-
-__device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, double& gx, double& gy, double& gz) {
-  const double v000 = c.q00.x, v001 = c.zlow ? c.q00.x : c.q00.y;
-  const double v010 = c.q01.x, v011 = c.zlow ? c.q01.x : c.q01.y;
-  const double v100 = c.q10.x, v101 = c.zlow ? c.q10.x : c.q10.y;
-  const double v110 = c.q11.x, v111 = c.zlow ? c.q11.x : c.q11.y;
-  // x-lerps; the x-differences feed grad x
-  const double e00 = v100 - v000, e01 = v101 - v001, e10 = v110 - v010, e11 = v111 - v011;
-  const double v00 = fma(c.dx, e00, v000), v01 = fma(c.dx, e01, v001);
-  const double v10 = fma(c.dx, e10, v010), v11 = fma(c.dx, e11, v011);
-  // y-lerps; y-differences feed grad y
-  const double f0 = v10 - v00, f1 = v11 - v01;
-  const double v0 = fma(c.dy, f0, v00), v1 = fma(c.dy, f1, v01);
-  const double h = v1 - v0;
-  const double d = fma(c.dz, h, v0);                      // :229
-  const double y = fma(c.dz, f1 - f0, f0);                // :232-233
-  const double ex0 = fma(c.dy, e10 - e00, e00), ex1 = fma(c.dy, e11 - e01, e01);
-  const double x = fma(c.dz, ex1 - ex0, ex0);             // :234-239
-  dist = c.in_map ? d : -1.0;                             // :187, H3
-  gx = c.in_map ? x : 0.0;
-  gy = c.in_map ? y : 0.0;
-  gz = c.in_map ? h : 0.0;                                // :231
-}
 
 // One step of the transposing reduction: every lane holds 2*H values; lanes whose `bit` is clear
 // keep the low H (and give away the high H), the others the opposite.  After the step each lane
@@ -185,9 +76,9 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const int q = lane >> 3, j = lane & 7;  // trajectory slot of the warp, lane within the quarter
 
-  // 2^(j/64) table for exp2_tab: the only block-level synchronisation of the kernel
+  // 2^(j/16) table for exp2_tab: the only block-level synchronisation of the kernel
   double* xtab = smem + wpc * kTrajPerWarp * traj_smem_doubles(m);
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) xtab[i] = exp2((double)i * (1.0 / 64.0));
+  exp2_tab_init(xtab, threadIdx.x, blockDim.x);
   __syncthreads();
 
   const int64_t b_raw = ((int64_t)blockIdx.x * wpc + warp) * kTrajPerWarp + q;
@@ -261,6 +152,7 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
         const double t = tt[k], t2 = tt[ns_cap + k], t3 = tt[2 * ns_cap + k], t4 = tt[3 * ns_cap + k],
                      t5 = tt[4 * ns_cap + k];
         double pos[3], vel[3];
+        float pf[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const double* c = cb + a * 6;
@@ -270,10 +162,11 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
           pa = __dadd_rn(pa, __dmul_rn(c[3], t3));
           pa = __dadd_rn(pa, __dmul_rn(c[4], t4));
           pa = __dadd_rn(pa, __dmul_rn(c[5], t5));
-          pos[a] = f32_round_trip(pa);
+          pf[a] = __double2float_rn(pa);
+          pos[a] = (double)pf[a];
         }
         SdfCell cell;
-        sdf_gather(S, pos[0], pos[1], pos[2], cell);  // 4 x LDG.128 in flight from here
+        sdf_gather(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const double* c = cb + a * 6;
@@ -383,17 +276,36 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
   }
 }
 
+bool eval_mma_applicable(const ProbLayout& PL, int64_t traj_offset, int64_t starts_per_problem);
+cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
+                            const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
+                            int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
+                            cudaStream_t stream);
+
+// GTOP_EVAL_KERNEL=general forces the quarter-warp kernel (tests exercise both); default: the DMMA
+// multi-start kernel whenever groups of 8 consecutive trajectories share a problem.
+static bool force_general() {
+  static const bool v = [] {
+    const char* e = std::getenv("GTOP_EVAL_KERNEL");
+    return e != nullptr && std::strcmp(e, "general") == 0;
+  }();
+  return v;
+}
+
 cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
                         const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
                         int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
                         int max_ctas, cudaStream_t stream) {
   (void)max_ctas;
   if (B <= 0) return cudaSuccess;
+  if (!force_general() && eval_mma_applicable(PL, traj_offset, starts_per_problem))
+    return launch_eval_mma(S, PL, prob, num_problems, E, X, B, traj_offset, starts_per_problem, cost, grad, oob_counter,
+                           stream);
   // warps per CTA: as many as keep the CTA's shared memory modest (4 CTAs/SM at 16 warps/SM)
   const size_t per_warp = sizeof(double) * (size_t)traj_smem_doubles(PL.m) * kTrajPerWarp;
   int wpc = kMaxWarpsPerCta;
   while (wpc > 1 && per_warp * wpc + 512 > 48 * 1024) wpc >>= 1;
-  const size_t smem = per_warp * wpc + 64 * sizeof(double);
+  const size_t smem = per_warp * wpc + kExpTab * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_eval_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -1,0 +1,305 @@
+// eval_mma_kernel.cu — cost + gradient of GTOP trajectories for MULTI-START batches on sm_100a:
+// groups of 8 consecutive trajectories share one problem (same waypoints / segment times), which is
+// BASELINE configs[2] (65,536 = 64 waypoint sets x 1,024 starts) and configs[4].
+//
+// Replaces GradTrajOptimizer::getCostAndGradient (src/grad_traj_optimizer.cpp:281-448 of the
+// reference), same maths as eval_kernel.cu; what changes is the work decomposition:
+//
+//   warp = 8 trajectories x 4 lanes.  Lane (g, j) = (lane >> 2, lane & 3) evaluates sample 4*it + j of
+//   trajectory g in iteration `it` of the current segment (8 iterations at N_s = 30).
+//
+//   * The per-sample contribution to the 3x6 moment block of the segment,
+//         U[a][i] += sA_a * tau_i + sB_a * tau'_i        (tau = t^i, tau' = i t^(i-1), :376-381)
+//     is a (8 trajectories x 4 samples) x (4 samples x 8 powers) product per axis and per kind, because
+//     tau/tau' only depend on the problem: it is issued as FP64 tensor-core tiles
+//     (mma.sync.m8n8k4.f64, SASS DMMA) — A fragment = the lane's own sA_a (or sB_a), B fragment = a
+//     host-built table, C fragment = 2 accumulators per axis.  The DMMA sums over the 4 lanes of a
+//     trajectory, so there is NO cross-lane shuffle reduction and the accumulators shrink from 19 to 6
+//     doubles per lane.  DMMA shares the FP64 pipe with DFMA on B200 (tools/fp64_peak.cu: 36.9 vs 34.0
+//     TFLOP/s, mixed = sum of both), so this does not buy FP64 throughput; it buys issue slots
+//     (6 DMMA instead of ~50 DFMA/DMUL per sample) and removes the shuffle/shared-memory traffic of
+//     the reduction — the general kernel is L1TEX- and issue-bound, not FP64-bound (profiles/).
+//   * Column c of the accumulation tiles carries power (c>>1) + 4(c&1): lane (g,j) ends up with the
+//     moments of powers (j, 4+j), which are exactly the A fragments of the two k-steps of the
+//     back-projection  G[a][r] = sum_i U[a][i] * dt*Linv[i][r]  (T*Ldp, :378-379) — two more DMMAs per
+//     axis, no data movement in between.
+//   * The back-projection columns alternate with the segment parity (deriv_of_col): the
+//     end-derivative columns of segment s are the start-derivative columns of segment s+1, so the
+//     gradient rows of an interior waypoint accumulate in place in the C fragment across the two
+//     segments that touch it and are written once.
+//   * Coefficients c = L d (:253-279) stay scalar, in the reference's summation order, unfused.
+//   * SDF corners come from the patch-ordered xy-quad copy of the grid: 2 x LDG.256 per sample.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "eval_common.cuh"
+#include "gtop_types.cuh"
+
+namespace gtop {
+
+#ifndef GTOP_MMA_MINB
+#define GTOP_MMA_MINB 5
+#endif
+constexpr int kMmaMaxWarps = 4;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// per-warp shared memory, in doubles:
+//   Wd   [8][wstride]   boundary derivatives per trajectory, [3][nrow] in waypoint order (nrow = 3(m+1));
+//                       wstride odd -> the 8 trajectories of a warp sit in distinct banks
+//   coef [15][8][2]     coefficient pairs of the current segment, 16-byte element per trajectory:
+//                       per axis (c0,c1) (c2,c3) (c4,c5) (2c2,3c3) (4c4,5c5)
+//   scr  [8][9]         finished collision-gradient rows of one waypoint (3 axes x p,v,a)
+__host__ __device__ inline int mma_wstride(int m) { return (9 * (m + 1)) | 1; }
+__host__ __device__ inline int mma_warp_smem_doubles(int m) { return 8 * mma_wstride(m) + 240 + 72; }
+
+// coefficients c[a][i] = sum_r Linv[i][r] * dseg[a][r], summed in ascending dense-column order of L
+// (start derivatives first, except for the last segment whose end derivatives live in columns 3..5
+// of d) with unfused mul/add — the same 6-term sum as `L * d` (:273).  Work item = (axis, power pair).
+template <bool kLast>
+__device__ __forceinline__ void coef_phase(const double* __restrict__ Wd, int nrow, int s,
+                                           const double2* __restrict__ LiTP, double2* __restrict__ coef, int g, int j) {
+  for (int item = j; item < 9; item += 4) {
+    const int a = item / 3, p = item - 3 * a;
+    const double* w0 = Wd + a * nrow + 3 * s;  // p0,v0,a0,pT,vT,aT contiguous in waypoint order
+    const double2* wt = LiTP + p * 6;
+    double q0[6], q1[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const double2 L = __ldg(wt + r);
+      const double w = w0[r];
+      q0[r] = __dmul_rn(L.x, w), q1[r] = __dmul_rn(L.y, w);
+    }
+    double c0, c1;
+    if (kLast) {
+      c0 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(q0[3], q0[4]), q0[5]), q0[0]), q0[1]), q0[2]);
+      c1 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(q1[3], q1[4]), q1[5]), q1[0]), q1[1]), q1[2]);
+    } else {
+      c0 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(q0[0], q0[1]), q0[2]), q0[3]), q0[4]), q0[5]);
+      c1 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(q1[0], q1[1]), q1[2]), q1[3]), q1[4]), q1[5]);
+    }
+    coef[(a * 5 + p) * 8 + g] = make_double2(c0, c1);
+    // e_k = k*c_k for the velocity polynomial (2*coeff(s,2), 3*coeff(s,3), ... :477-485)
+    if (p >= 1)
+      coef[(a * 5 + 2 + p) * 8 + g] = make_double2(__dmul_rn((double)(2 * p), c0), __dmul_rn((double)(2 * p + 1), c1));
+  }
+}
+
+__global__ void __launch_bounds__(kMmaMaxWarps * 32, GTOP_MMA_MINB)
+k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_problems, EvalScalars E,
+           const double* __restrict__ X, int64_t B, int64_t traj_offset, int64_t starts_per_problem,
+           double* __restrict__ cost_out, double* __restrict__ grad_out, unsigned long long* __restrict__ oob_counter) {
+  extern __shared__ __align__(16) double smem[];
+  const int m = PL.m, P = PL.P, n = PL.n, nrow = 3 * (m + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int g = lane >> 2, j = lane & 3;  // trajectory slot of the warp, sample slot of the iteration
+  const int wstride = mma_wstride(m), per_warp = mma_warp_smem_doubles(m);
+
+  // 2^(j/16) table for exp2_tab: the only block-level synchronisation of the kernel
+  double* xtab = smem + wpc * per_warp;
+  exp2_tab_init(xtab, threadIdx.x, blockDim.x);
+  __syncthreads();
+
+  // Groups of 8 are aligned on the GLOBAL trajectory index (traj_offset + b), so that any split of a
+  // batch evaluates every trajectory in the same lane group with the same instructions: results are
+  // bit-identical for every partition of the batch across calls / GPUs.
+  const int64_t gb0 = traj_offset - (traj_offset & 7) + ((int64_t)blockIdx.x * wpc + warp) * 8;
+  if (gb0 >= traj_offset + B) return;                // the whole warp is past the end
+  const int64_t b_raw = gb0 + g - traj_offset;
+  const bool live = b_raw >= 0 && b_raw < B;         // ragged head / tail: dead slots shadow a live
+  const int64_t b = b_raw < 0 ? 0 : (b_raw < B ? b_raw : B - 1);  // trajectory of the same group
+
+  double* wbase = smem + warp * per_warp;
+  double* Wd = wbase + g * wstride;
+  double2* coef = reinterpret_cast<double2*>(wbase + 8 * wstride);
+  double* scr = wbase + 8 * wstride + 240 + g * 9;
+
+  // all 8 trajectories of the group belong to one problem (host-checked: starts_per_problem % 8 == 0)
+  const int64_t pid = (gb0 / starts_per_problem) % num_problems;
+  const double* __restrict__ pr = prob + pid * (int64_t)PL.stride;
+  const double* __restrict__ x = X + b * n;
+
+  // ---- 1. boundary derivatives in waypoint order --------------------------------------------------
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int jj = j; jj < P; jj += 4) Wd[a * nrow + 3 + jj] = x[a * P + jj];
+  for (int o = j; o < 18; o += 4) {
+    const int a = o / 6, r = o - 6 * a;
+    Wd[a * nrow + (r < 3 ? r : 3 * m + (r - 3))] = pr[PL.off_Df + o];
+  }
+  __syncwarp();
+
+  double G[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // back-projected gradient rows (C fragments)
+  double Jc = 0.0;
+  unsigned oob = 0;
+  const double kA = -E.alpha * E.alpha_over_r * S.res_inv;  // gd*cd = -(alpha^2/r) e^2; grad scale 1/res
+  double* __restrict__ gout = grad_out + b * n;
+
+  for (int s = 0; s < m; ++s) {
+    if (!E.skip_collision) {
+      const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + s * 36);
+      if (s == m - 1) coef_phase<true>(Wd, nrow, s, LiTP, coef, g, j);
+      else coef_phase<false>(Wd, nrow, s, LiTP, coef, g, j);
+      __syncwarp();
+
+      const int ns = (int)pr[PL.off_ns + s];
+      const int nit = (ns + 3) >> 2;
+      const double2* __restrict__ T6 = reinterpret_cast<const double2*>(pr + PL.off_T6 + (s * PL.nsp + j) * 6);
+      const double2* __restrict__ BF = reinterpret_cast<const double2*>(pr + PL.off_BF + s * PL.nsp * 16 + lane * 2);
+
+      double U[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // moment accumulators (C fragments)
+      double jseg = 0.0;
+      for (int it = 0; it < nit; ++it) {
+        const double2 ta = __ldg(T6 + it * 12), tb = __ldg(T6 + it * 12 + 1), tc = __ldg(T6 + it * 12 + 2);
+        const double2 bf = __ldg(BF + it * 32);
+        const double t = ta.x, t2 = ta.y, t3 = tb.x, t4 = tb.y, t5 = tc.x, w = tc.y;
+        double pos[3], vel[3], c1[3];
+        float pf[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double2 c01 = coef[(a * 5 + 0) * 8 + g], c23 = coef[(a * 5 + 1) * 8 + g], c45 = coef[(a * 5 + 2) * 8 + g];
+          // getPositionFromCoeff (:457-465): left-to-right, unfused, then float
+          double pa = __dadd_rn(c01.x, __dmul_rn(c01.y, t));
+          pa = __dadd_rn(pa, __dmul_rn(c23.x, t2));
+          pa = __dadd_rn(pa, __dmul_rn(c23.y, t3));
+          pa = __dadd_rn(pa, __dmul_rn(c45.x, t4));
+          pa = __dadd_rn(pa, __dmul_rn(c45.y, t5));
+          pf[a] = __double2float_rn(pa);
+          pos[a] = (double)pf[a];
+          c1[a] = c01.y;
+        }
+        SdfCell cell;
+        sdf_gather(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double2 e01 = coef[(a * 5 + 3) * 8 + g], e23 = coef[(a * 5 + 4) * 8 + g];
+          // getVelocityFromCoeff (:477-485)
+          double va = __dadd_rn(c1[a], __dmul_rn(e01.x, t));
+          va = __dadd_rn(va, __dmul_rn(e01.y, t2));
+          va = __dadd_rn(va, __dmul_rn(e23.x, t3));
+          va = __dadd_rn(va, __dmul_rn(e23.y, t4));
+          vel[a] = f32_round_trip(va);
+        }
+        const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], vel[0] * vel[0]));
+        const double vnorm = sqrt_pos(fmax(vn2, 1e-300)) + 1e-5;  // :358 (sqrt(1e-300) is absorbed by 1e-5)
+        const double inv_vn = rcp_pos(vnorm);
+
+        double dist, gd[3];
+        sdf_finish(cell, dist, gd[0], gd[1], gd[2]);
+        oob += (!cell.in_map && 4 * it + j < ns) ? 1u : 0u;
+
+        // exp(-(d-d0)/r) (:509/:514) = 2^((d0-d)*log2(e)/r); d <= 10000 so clamp the exponent
+        const double ee =
+            exp2_tab(fmin(fmax(fma(dist, E.neg_log2e_over_r, E.d0_log2e_over_r), -1000.0), 1000.0), xtab);
+        const double ev = ee * vnorm;
+        jseg = fma(w, ev, jseg);           // cost: cd*|v| = alpha*ee*vnorm (alpha, dt applied later)
+        // sA_a = gd*grad_a*cd*|v| = kA * ee^2 * vnorm * g_a      (:378, extra cd reproduced — H4)
+        // sB_a = cd*v_a/|v|       = alpha * ee * v_a / vnorm     (:379)
+        const double sAc = kA * (ee * ev);
+        const double sBc = E.alpha * (ee * inv_vn);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          dmma884(U[a][0], U[a][1], sAc * gd[a], bf.x);   // += sA_a(sample) * tau_i(sample)
+          dmma884(U[a][0], U[a][1], sBc * vel[a], bf.y);  // += sB_a(sample) * tau'_i(sample)
+        }
+      }
+      Jc = fma(jseg, pr[PL.off_dt + s], Jc);
+
+      // ---- back-projection through dt*Linv_s: the C fragments of U are the A fragments here -------
+      const double lb0 = pr[PL.off_LB + s * 64 + lane], lb1 = pr[PL.off_LB + s * 64 + 32 + lane];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        dmma884(G[a][0], G[a][1], U[a][0], lb0);  // powers 0..3
+        dmma884(G[a][0], G[a][1], U[a][1], lb1);  // powers 4,5 (6,7 are zero)
+      }
+    }
+
+    // ---- the rows of waypoint s (start derivatives of segment s) are complete -----------------------
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int r = deriv_of_col(2 * j + e, s);
+      if (r >= 0 && r < 3) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          scr[a * 3 + r] = G[a][e];  // s = 0: the fixed start state, never read
+          G[a][e] = 0.0;
+        }
+      }
+    }
+    __syncwarp();
+    if (s >= 1) {
+      // smoothness rows 2 Rfp' df + 2 Rpp dp (:330-332) from the band of R, combined with the collision
+      // rows and written out (:425-431): 9 values per trajectory over its 4 lanes
+      for (int o = j; o < 9; o += 4) {
+        const int a = o / 3, r = o - 3 * a, jj = 3 * (s - 1) + r;
+        const double* __restrict__ band = pr + PL.off_Rg + jj * 9;
+        const double* Wb = Wd + a * nrow + 3 * (s - 1);
+        double gs = 0.0;
+#pragma unroll
+        for (int u = 0; u < 9; ++u) gs = fma(Wb[u], band[u], gs);
+        const double val = (E.ws * (2.0 * gs) + E.wc * scr[o]) + 1e-5;
+        if (live) gout[a * P + jj] = val;
+      }
+      __syncwarp();
+    }
+  }
+  if (oob_counter != nullptr) {
+    oob = __reduce_add_sync(kFull, live ? oob : 0u);
+    if (lane == 0 && oob) atomicAdd(oob_counter, (unsigned long long)oob);
+  }
+
+  // ---- smoothness cost: banded column sums of R in waypoint order (:326-327) -----------------------
+  double js = 0.0;
+  for (int u = j; u < nrow; u += 4) {
+    const double* __restrict__ band = pr + PL.off_Rc + u * 9;
+    const int base = 3 * (u / 3 - 1);
+    const int j0 = base < 0 ? 3 : 0, j1 = (base + 9 > nrow) ? 6 : 9;
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+    for (int jj = j0; jj < j1; ++jj) {
+      const double bv = band[jj];
+      y0 = fma(Wd[base + jj], bv, y0);
+      y1 = fma(Wd[nrow + base + jj], bv, y1);
+      y2 = fma(Wd[2 * nrow + base + jj], bv, y2);
+    }
+    js = fma(y0, Wd[u], js);
+    js = fma(y1, Wd[nrow + u], js);
+    js = fma(y2, Wd[2 * nrow + u], js);
+  }
+#pragma unroll
+  for (int o = 2; o > 0; o >>= 1) {
+    js += __shfl_xor_sync(kFull, js, o);
+    Jc += __shfl_xor_sync(kFull, Jc, o);
+  }
+  if (live && j == 0) cost_out[b] = E.ws * js + E.wc * (E.alpha * Jc) + 1e-3;  // :417-418
+}
+
+bool eval_mma_applicable(const ProbLayout& PL, int64_t traj_offset, int64_t starts_per_problem) {
+  (void)PL, (void)traj_offset;
+  return starts_per_problem % 8 == 0;
+}
+
+cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
+                            const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
+                            int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
+                            cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  // warps per CTA: as many as keep the CTA's shared memory modest (several CTAs per SM)
+  const size_t per_warp = sizeof(double) * (size_t)mma_warp_smem_doubles(PL.m);
+  int wpc = kMmaMaxWarps;
+  while (wpc > 1 && per_warp * wpc + 512 > 40 * 1024) wpc >>= 1;
+  const size_t smem = per_warp * wpc + kExpTab * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_eval_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int64_t per_cta = (int64_t)wpc * 8;
+  const int64_t grid = ((traj_offset & 7) + B + per_cta - 1) / per_cta;
+  k_eval_mma<<<(unsigned)grid, wpc * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset,
+                                                         starts_per_problem, cost, grad, oob_counter);
+  return cudaGetLastError();
+}
+
+}  // namespace gtop

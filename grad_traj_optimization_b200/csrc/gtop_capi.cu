@@ -21,7 +21,7 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
                         int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
                         int max_ctas, cudaStream_t stream);
 cudaError_t launch_fill(double* dist, uint8_t* occ, int64_t n, double dval, cudaStream_t st);
-cudaError_t launch_build_pairs(const double* dist, double2* pair, int64_t n, int nz, cudaStream_t st);
+cudaError_t launch_build_quads(const SdfView& S, const double* dist, void* quad, cudaStream_t st);
 cudaError_t launch_set_occupancy(const SdfView& S, uint8_t* occ, const double* pts_dev, int64_t n, cudaStream_t st);
 cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t* boxes_dev, int64_t n,
                              cudaStream_t st);
@@ -58,7 +58,7 @@ struct gtop_sdf {
   double origin[3], map_size[3];
   int64_t nvox = 0;
   double* dist = nullptr;
-  double2* pair = nullptr;  // z-pair copy of dist, rebuilt whenever dist changes
+  void* quad = nullptr;  // xy-quad copy of dist (SdfView::quad), rebuilt whenever dist changes
   uint8_t* occ = nullptr;
   int32_t *d1 = nullptr, *d2 = nullptr;
   cudaStream_t stream = nullptr;
@@ -161,20 +161,27 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
       return fail(GTOP_E_INVALID, "grid dimension out of range [1, 16384]");
     }
   }
-  if ((int64_t)g[0] * g[1] * g[2] > 2147483647LL) {
+  if ((int64_t)g[0] * g[1] * g[2] > 2147483647LL || quad_elems(g[0], g[1], g[2]) > 2147483647LL) {
     delete s;
     return fail(GTOP_E_INVALID, "more than 2^31-1 voxels");
   }
   SdfView& v = s->view;
   v.nx = g[0], v.ny = g[1], v.nz = g[2];
+  v.nxh = (g[0] + 1) / 2, v.nyh = (g[1] + 1) / 2;
   v.ox = origin[0], v.oy = origin[1], v.oz = origin[2];
   v.res = resolution, v.res_inv = 1 / resolution, v.half_res = 0.5 * resolution;
   v.lox = origin[0] + 1e-4, v.loy = origin[1] + 1e-4, v.loz = origin[2] + 1e-4;  // sdf_map.cpp:56-57
   v.hix = (origin[0] + map_size[0]) - 1e-4, v.hiy = (origin[1] + map_size[1]) - 1e-4,
   v.hiz = (origin[2] + map_size[2]) - 1e-4;  // :62-63 with max_range = origin + map_size (:12)
+  {  // float images of the isInMap bounds (exact for float-valued positions, see SdfView)
+    auto up = [](double b) { float f = (float)b; return (double)f < b ? std::nextafterf(f, INFINITY) : f; };
+    auto down = [](double b) { float f = (float)b; return (double)f > b ? std::nextafterf(f, -INFINITY) : f; };
+    v.lofx = up(v.lox), v.lofy = up(v.loy), v.lofz = up(v.loz);
+    v.hifx = down(v.hix), v.hify = down(v.hiy), v.hifz = down(v.hiz);
+  }
   s->nvox = (int64_t)g[0] * g[1] * g[2];
   cudaError_t e = cudaMalloc(&s->dist, sizeof(double) * s->nvox);
-  if (e == cudaSuccess) e = cudaMalloc(&s->pair, sizeof(double2) * s->nvox);
+  if (e == cudaSuccess) e = cudaMalloc(&s->quad, 32 * (size_t)quad_elems(g[0], g[1], g[2]));
   if (e == cudaSuccess) e = cudaMalloc(&s->occ, s->nvox);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
@@ -183,9 +190,9 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
     return fail(GTOP_E_ALLOC, std::string("sdf allocation: ") + cudaGetErrorString(e));
   }
   v.dist = s->dist;
-  v.pair = s->pair;
+  v.quad = s->quad;
   CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));  // sdf_map.cpp:22-23
-  CU(launch_build_pairs(s->dist, s->pair, s->nvox, v.nz, s->stream));
+  CU(launch_build_quads(v, s->dist, s->quad, s->stream));
   g_launches += 2;
   CU(cudaStreamSynchronize(s->stream));
   *out = s;
@@ -195,7 +202,7 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
 int gtop_sdf_destroy(gtop_sdf* s) {
   if (!s) return GTOP_OK;
   cudaSetDevice(s->device);
-  cudaFree(s->dist), cudaFree(s->pair), cudaFree(s->occ), cudaFree(s->d1), cudaFree(s->d2);
+  cudaFree(s->dist), cudaFree(s->quad), cudaFree(s->occ), cudaFree(s->d1), cudaFree(s->d2);
   for (auto& e : s->ev)
     if (e) cudaEventDestroy(e);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -213,7 +220,7 @@ int gtop_sdf_reset(gtop_sdf* s) {
   REQUIRE(s, "null sdf");
   CU(cudaSetDevice(s->device));
   CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));
-  CU(launch_build_pairs(s->dist, s->pair, s->nvox, s->view.nz, s->stream));
+  CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   g_launches += 2;
   CU(cudaStreamSynchronize(s->stream));
   return GTOP_OK;
@@ -260,7 +267,7 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
   CU(launch_edt(s->occ, s->d1, s->d2, s->dist, s->view.nx, s->view.ny, s->view.nz, s->view.res, s->dist_fresh, s->stream,
                 s->ev));
   s->dist_fresh = false;
-  CU(launch_build_pairs(s->dist, s->pair, s->nvox, s->view.nz, s->stream));
+  CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   g_launches += 4;
   CU(cudaStreamSynchronize(s->stream));
   for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&s->last_ms[i], s->ev[i], s->ev[i + 1]);
@@ -284,7 +291,7 @@ int gtop_sdf_upload_distance(gtop_sdf* s, const double* host) {
   REQUIRE(s && host, "null argument");
   CU(cudaSetDevice(s->device));
   CU(cudaMemcpy(s->dist, host, sizeof(double) * s->nvox, cudaMemcpyHostToDevice));
-  CU(launch_build_pairs(s->dist, s->pair, s->nvox, s->view.nz, s->stream));
+  CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   ++g_launches;
   CU(cudaStreamSynchronize(s->stream));
   return GTOP_OK;

@@ -4,24 +4,43 @@
 
 #include <cstdint>
 
+#if defined(__CUDACC__)
+#define GTOP_HD __host__ __device__
+#else
+#define GTOP_HD
+#endif
+
 namespace gtop {
 
 // View of an SDFMap resident in HBM.  Index of voxel (x,y,z) is x*ny*nz + y*nz + z, as in the
 // reference (sdf_map.cpp:92,97-98): z is the fastest axis.
 struct SdfView {
   const double* dist;  // nx*ny*nz fp64 distances
-  // z-pair copy of the same field: pair[i] = (dist[x,y,z], dist[x,y,min(z+1,nz-1)]) as one 16-byte
-  // element, so the two z-corners of a trilinear cell come from ONE aligned 128-bit load whatever
-  // the parity of z (z is the fastest axis).  2x the footprint (32 MB for the 200x200x50 map:
-  // still L2-resident), half the gather instructions / L1 wavefronts.
-  const double2* pair;
+  // xy-quad copy of the same field for the evaluation kernels' 256-bit gathers: one 32-byte element
+  // per voxel, quad(x,y,z) = (D[x,y,z], D[x,y+,z], D[x+,y,z], D[x+,y+,z]) with x+ = min(x+1,nx-1),
+  // y+ = min(y+1,ny-1): the four (x,y) corners of a trilinear cell at one height are ONE aligned
+  // LDG.256, a sample needs two (z0, z1).  Elements are stored in 2x2 (x,y) patches,
+  //   index = ((((x>>1)*nyh + (y>>1))*nz + z) << 2) + ((x&1)<<1) + (y&1),
+  // so a 128-byte line holds the quads of a 2x2 patch at one height and the z-neighbour is the next
+  // line: consecutive samples of a trajectory (about half a voxel apart, mostly horizontal motion)
+  // fall into the same lines.  Measured on B200 (tools/gather_bench.cu): 35 L1 wavefronts per
+  // 32-sample gather against 76 for four 128-bit loads from a z-pair layout.  4x the footprint of
+  // `dist` (64 MB for the 200x200x50 map).
+  const void* quad;
   int nx, ny, nz;
+  int nxh, nyh;             // ceil(nx/2), ceil(ny/2): patch grid of the quad copy
   double ox, oy, oz;        // origin
   double res, res_inv;      // resolution, 1/resolution (sdf_map.cpp:6-7)
   double half_res;          // 0.5*resolution (sdf_map.cpp:201)
   double lox, loy, loz;     // min_range + 1e-4   (isInMap, sdf_map.cpp:56-57)
   double hix, hiy, hiz;     // max_range - 1e-4   (sdf_map.cpp:62-63)
+  // the same bounds for a float-valued position p: p < lo  <=>  p < lof (smallest float >= lo),
+  // p > hi <=> p > hif (largest float <= hi).  Sample positions are float-valued (:457-467).
+  float lofx, lofy, lofz, hifx, hify, hifz;
 };
+
+// number of 32-byte quad elements of a grid (patch-padded)
+inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 2) * ((ny + 1) / 2) * nz * 4; }
 
 // Per-problem record in HBM: `stride` doubles per problem, sections at the offsets below.
 //   dt    [m]            T_s / N_s                               (grad_traj_optimizer.cpp:351)
@@ -35,14 +54,33 @@ struct SdfView {
 //   Df    [3][6]         fixed derivatives per axis: p0,v0,a0,pEnd,vEnd,aEnd
 //   LinvT [m][6][6]      transpose of Linv (col = power): the coefficient step reads 6 contiguous
 //                        doubles per derivative instead of a stride-6 column
+// Sections read by the multi-start kernel k_eval_mma (eval_mma_kernel.cu); nsp = ns_cap rounded up to 4:
+//   T6    [m][nsp][6]    per sample slot (t, t^2, t^3, t^4, t^5, w): w = 1 for a real sample, 0 for a
+//                        padding slot (which repeats the last real sample's times)
+//   BF    [m][nsp/4][32][2]  B fragments of the accumulation DMMAs: lane 4g+j of iteration `it` holds
+//                        (tau, tau') of sample 4*it+j for power kPowerOfCol[g]  (tau_i = t^i,
+//                        tau'_i = i t^(i-1), :379; zeros for padding slots and powers 6,7)
+//   LB    [m][2][32]     B fragments of the back-projection DMMAs: dt_s * Linv_s[4*ks + j][r(g)], where
+//                        column g <-> local derivative r alternates with the segment parity so that the
+//                        end-derivative columns of segment s are the start-derivative columns of s+1
+//   LiTP  [m][3][6][2]   (Linv[2p][r], Linv[2p+1][r]): coefficient step, two powers per 128-bit load
 struct ProbLayout {
   int m;       // segments
   int P;       // free derivatives per axis = 3(m-1)
   int n;       // NLopt variables = 3P
   int ns_cap;  // samples_per_segment (table capacity)
+  int nsp;     // ns_cap rounded up to a multiple of 4
   int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df, off_LinvT;
+  int off_T6, off_BF, off_LB, off_LiTP;
   int stride;
 };
+
+// column c of the accumulation DMMAs carries power kPowerOfCol[c]: lane (g,j) then ends up holding the
+// moments of powers (j, 4+j) — exactly the A fragments of the two back-projection k-steps.
+GTOP_HD inline int power_of_col(int c) { return (c >> 1) + 4 * (c & 1); }
+// local derivative (natural order p0,v0,a0,pT,vT,aT) carried by column c of the back-projection DMMAs
+// of segment s; -1 for the two padding columns
+GTOP_HD inline int deriv_of_col(int c, int s) { return c >= 6 ? -1 : ((s & 1) ? (c + 3) % 6 : c); }
 
 inline ProbLayout make_layout(int m, int ns_cap) {
   ProbLayout L;
@@ -59,6 +97,12 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   L.off_Rg = o, o += (3 * m - 3) * 9;
   L.off_Df = o, o += 18;
   L.off_LinvT = o, o += m * 36;
+  o = (o + 1) & ~1;
+  L.nsp = (ns_cap + 3) & ~3;
+  L.off_T6 = o, o += m * L.nsp * 6;
+  L.off_BF = o, o += m * L.nsp * 16;
+  L.off_LB = o, o += m * 64;
+  L.off_LiTP = o, o += m * 36;
   L.stride = (o + 1) & ~1;  // keep every record 16-byte aligned
   return L;
 }

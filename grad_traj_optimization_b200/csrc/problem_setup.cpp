@@ -289,6 +289,37 @@ void pack_record(const ProblemHost& p, double* rec) {
   for (int s = 0; s < p.m; ++s)
     for (int i = 0; i < 6; ++i)
       for (int r = 0; r < 6; ++r) rec[L.off_LinvT + s * 36 + r * 6 + i] = p.Linv[(size_t)s * 36 + i * 6 + r];
+  // ---- tables of the multi-start (DMMA) kernel ------------------------------------------------
+  const int NS = p.ns_cap, NSP = L.nsp;
+  for (int s = 0; s < p.m; ++s) {
+    const double* tt = &p.tt[(size_t)s * 5 * NS];
+    const int ns = (int)p.ns[s];
+    for (int k = 0; k < NSP; ++k) {
+      const int ks = ns > 0 ? (k < ns ? k : ns - 1) : -1;  // padding slots repeat the last real sample
+      double pw[8] = {1.0, 0, 0, 0, 0, 0, 0, 0};           // tau_i = t^i                  (:549)
+      for (int q = 1; q <= 5; ++q) pw[q] = ks >= 0 ? tt[(size_t)(q - 1) * NS + ks] : 0.0;
+      double* t6 = rec + L.off_T6 + ((size_t)s * NSP + k) * 6;
+      for (int q = 1; q <= 5; ++q) t6[q - 1] = pw[q];
+      t6[5] = k < ns ? 1.0 : 0.0;
+      const bool real = k < ns;
+      for (int g = 0; g < 8; ++g) {
+        const int i = power_of_col(g);
+        double* bf = rec + L.off_BF + (size_t)s * NSP * 16 + (size_t)(k >> 2) * 64 + (size_t)(4 * g + (k & 3)) * 2;
+        bf[0] = (real && i < 6) ? pw[i] : 0.0;
+        bf[1] = (real && i >= 1 && i < 6) ? (double)i * pw[i - 1] : 0.0;  // T*V: tau'_i = i t^(i-1)  (:379)
+      }
+    }
+    for (int ks = 0; ks < 2; ++ks)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, i = 4 * ks + (lane & 3), r = deriv_of_col(g, s);
+        rec[L.off_LB + s * 64 + ks * 32 + lane] = (i < 6 && r >= 0) ? p.dt[s] * p.Linv[(size_t)s * 36 + i * 6 + r] : 0.0;
+      }
+    for (int pp = 0; pp < 3; ++pp)
+      for (int r = 0; r < 6; ++r) {
+        rec[L.off_LiTP + s * 36 + (pp * 6 + r) * 2 + 0] = p.Linv[(size_t)s * 36 + (2 * pp) * 6 + r];
+        rec[L.off_LiTP + s * 36 + (pp * 6 + r) * 2 + 1] = p.Linv[(size_t)s * 36 + (2 * pp + 1) * 6 + r];
+      }
+  }
 }
 
 void coeff_from_x(const ProblemHost& p, const double* x, double* coeff) {

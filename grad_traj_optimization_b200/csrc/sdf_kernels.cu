@@ -37,15 +37,32 @@ __global__ void k_fill(double* __restrict__ dist, uint8_t* __restrict__ occ, int
   }
 }
 
-// z-pair copy of the distance field for the evaluation kernel's 128-bit gathers (see SdfView::pair)
-__global__ void k_build_pairs(const double* __restrict__ dist, double2* __restrict__ pair, int64_t n, int nz) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int z = (int)(i % nz);
-    const double a = dist[i];
-    const double b = (z + 1 < nz) ? dist[i + 1] : a;
-    pair[i] = make_double2(a, b);
-  }
+// xy-quad copy of the distance field for the evaluation kernels' 256-bit gathers (see SdfView::quad).
+// Thread per (2x2 patch, z), adjacent threads on adjacent z: the 3x3 neighbourhood columns are read
+// coalesced along z, each thread writes the patch's four quads = one 128-byte line.
+__global__ void __launch_bounds__(256)
+k_build_quads(const double* __restrict__ dist, double2* __restrict__ quad, int nx, int ny, int nz, int nyh, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int z = (int)(i % nz);
+  const int64_t patch = i / nz;
+  const int x = 2 * (int)(patch / nyh), y = 2 * (int)(patch % nyh);
+  double v[3][3];
+#pragma unroll
+  for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int xx = min(x + dx, nx - 1), yy = min(y + dy, ny - 1);
+      v[dx][dy] = dist[((int64_t)xx * ny + yy) * nz + z];
+    }
+  double2* q = quad + i * 8;  // 4 quads x 2 double2
+#pragma unroll
+  for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+    for (int sy = 0; sy < 2; ++sy) {
+      q[(sx * 2 + sy) * 2 + 0] = make_double2(v[sx][sy], v[sx][sy + 1]);
+      q[(sx * 2 + sy) * 2 + 1] = make_double2(v[sx + 1][sy], v[sx + 1][sy + 1]);
+    }
 }
 
 __global__ void k_set_occupancy(SdfView S, uint8_t* __restrict__ occ, const double* __restrict__ pts, int64_t n) {
@@ -232,8 +249,9 @@ cudaError_t launch_fill(double* dist, uint8_t* occ, int64_t n, double dval, cuda
   return cudaGetLastError();
 }
 
-cudaError_t launch_build_pairs(const double* dist, double2* pair, int64_t n, int nz, cudaStream_t st) {
-  k_build_pairs<<<148 * 16, 256, 0, st>>>(dist, pair, n, nz);
+cudaError_t launch_build_quads(const SdfView& S, const double* dist, void* quad, cudaStream_t st) {
+  const int64_t n = (int64_t)S.nxh * S.nyh * S.nz;
+  k_build_quads<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dist, (double2*)quad, S.nx, S.ny, S.nz, S.nyh, n);
   return cudaGetLastError();
 }
 
