@@ -46,24 +46,27 @@ __device__ __forceinline__ double rcp_pos(double a) {
   return fma(y, fma(e, e, e), y);
 }
 
-// 2^y for y in [-1000, 1000]: y = k + j/16 + r, |r| <= 1/32; 2^y = 2^k * T[j] * 2^r with a degree-6
-// Taylor polynomial for 2^r (truncation (ln2/32)^7/7! = 4e-16).  T = 2^(j/16), 16 doubles = one
-// conflict-free shared-memory wavefront per warp.
+// 2^y for |y| < 2^26: y = k + j/16 + r, |r| <= 1/32; 2^y = 2^k * T[j] * 2^r with a degree-6 Taylor
+// polynomial for 2^r (truncation (ln2/32)^7/7! = 4e-16).  T = 2^(j/16), 16 doubles = one conflict-free
+// shared-memory wavefront per warp.  The exponent k is clamped to [-1000, 1000] in the integer domain
+// (r stays the true remainder): results below 2^-1000 come out as ~2^-1000 instead of 0, which is
+// far below anything the cost can resolve, and there is no FP64 min/max (a 6-instruction emulation).
 constexpr int kExpTab = 16;
+// ln2^k/k!, k = 6..1, in the constant bank: the DFMAs take them as c[][] operands (as immediates the
+// compiler re-materialises each 64-bit constant with two UMOVs per use)
+__constant__ double kExp2Poly[6] = {1.5403530393381609e-4, 1.3333558146428443e-3, 9.6181291076284772e-3,
+                                    5.5504108664821580e-2, 2.4022650695910071e-1, 6.9314718055994531e-1};
 __device__ __forceinline__ void exp2_tab_init(double* T, int tid, int nthreads) {
   for (int i = tid; i < kExpTab; i += nthreads) T[i] = exp2((double)i * (1.0 / kExpTab));
 }
 __device__ __forceinline__ double exp2_tab(double y, const double* __restrict__ T) {
   const double kMagic = 422212465065984.0;  // 1.5 * 2^48: ulp = 1/16
   const double z = y + kMagic;
-  const int N = __double2loint(z);          // round(y*16)
+  const int N = max(min(__double2loint(z), 16000), -16000);  // round(y*16), clamped
   const double r = y - (z - kMagic);
-  double p = 1.5403530393381609e-4;           // ln2^6/6!
-  p = fma(p, r, 1.3333558146428443e-3);       // ln2^5/5!
-  p = fma(p, r, 9.6181291076284772e-3);       // ln2^4/4!
-  p = fma(p, r, 5.5504108664821580e-2);       // ln2^3/3!
-  p = fma(p, r, 2.4022650695910071e-1);       // ln2^2/2!
-  p = fma(p, r, 6.9314718055994531e-1);       // ln2
+  double p = kExp2Poly[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) p = fma(p, r, kExp2Poly[i]);
   const double tj = T[N & (kExpTab - 1)];
   const double m = fma(tj * r, p, tj);        // T[j] * (1 + r*p)
   return __hiloint2double(__double2hiint(m) + ((N >> 4) << 20), __double2loint(m));
@@ -75,10 +78,36 @@ __device__ __forceinline__ double f32_round_trip(double x) { return (double)__do
 struct __align__(32) Quad {
   double v00, v01, v10, v11;  // (x0,y0) (x0,y1) (x1,y0) (x1,y1) at one height
 };
+// L1 policy of the corner gathers (GTOP_GATHER_L1: 0 default, 1 no_allocate, 2 evict_first): the
+// gathers stream ~8 KB per warp and iteration through L1; keeping them from displacing the small
+// per-problem tables is what matters (see ldg_tab)
+#ifndef GTOP_GATHER_L1
+#define GTOP_GATHER_L1 1
+#endif
+#ifndef GTOP_TABLE_L1
+#define GTOP_TABLE_L1 1
+#endif
 __device__ __forceinline__ Quad ldg_quad(const void* p) {
   Quad q;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q.v00), "=d"(q.v01), "=d"(q.v10), "=d"(q.v11) : "l"(p));
+#if GTOP_GATHER_L1 == 1
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+#elif GTOP_GATHER_L1 == 2
+  asm volatile("ld.global.nc.L1::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+#else
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+#endif
+               : "=d"(q.v00), "=d"(q.v01), "=d"(q.v10), "=d"(q.v11) : "l"(p));
   return q;
+}
+// 128-bit load from a per-problem table (sample times, fragments): kept in L1 with evict_last
+__device__ __forceinline__ double2 ldg_tab(const double2* p) {
+#if GTOP_TABLE_L1 == 1
+  double2 v;
+  asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
 }
 
 // SDFMap::getDistWithGradTrilinear (sdf_map.cpp:185-242), split in two so that the caller can put
@@ -98,6 +127,7 @@ struct SdfCell {
   Quad q0, q1;  // heights z0, z1
   double dx, dy, dz;
   bool in_map, xlow, ylow;
+  bool special;  // !in_map || xlow || ylow: needs the select path of sdf_finish (rare: map border)
 };
 
 __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double py, double pz, float fx32, float fy32,
@@ -109,41 +139,56 @@ __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double p
   const double fy = floor(__dmul_rn(__dsub_rn(__dsub_rn(py, S.half_res), S.oy), S.res_inv));
   const double fz = floor(__dmul_rn(__dsub_rn(__dsub_rn(pz, S.half_res), S.oz), S.res_inv));
   // idx_pos = (idx + 0.5)*res + origin; diff = (pos - idx_pos)*res_inv     (:76-78, :209)
-  const double dx = __dmul_rn(__dsub_rn(px, __dadd_rn(__dmul_rn(__dadd_rn(fx, 0.5), S.res), S.ox)), S.res_inv);
-  const double dy = __dmul_rn(__dsub_rn(py, __dadd_rn(__dmul_rn(__dadd_rn(fy, 0.5), S.res), S.oy)), S.res_inv);
+  c.dx = __dmul_rn(__dsub_rn(px, __dadd_rn(__dmul_rn(__dadd_rn(fx, 0.5), S.res), S.ox)), S.res_inv);
+  c.dy = __dmul_rn(__dsub_rn(py, __dadd_rn(__dmul_rn(__dadd_rn(fy, 0.5), S.res), S.oy)), S.res_inv);
   c.dz = __dmul_rn(__dsub_rn(pz, __dadd_rn(__dmul_rn(__dadd_rn(fz, 0.5), S.res), S.oz)), S.res_inv);
   const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
   c.xlow = ix < 0, c.ylow = iy < 0;
-  c.dx = c.xlow ? 0.0 : dx;
-  c.dy = c.ylow ? 0.0 : dy;
+  c.special = !c.in_map || ((ix | iy) < 0);
   // the clamps also keep the loads of an out-of-map sample inside the buffer: no branch needed
   const int x0 = max(min(ix, S.nx - 1), 0), y0 = max(min(iy, S.ny - 1), 0);
   const int z0 = max(min(iz, S.nz - 1), 0), z1 = max(min(iz + 1, S.nz - 1), 0);
   const int e0 = ((((x0 >> 1) * S.nyh + (y0 >> 1)) * S.nz + z0) << 2) + ((x0 & 1) << 1) + (y0 & 1);
+#ifdef GTOP_EXP_NOGATHER  // timing experiment only: every lane reads the same two lines
+  const char* p = (const char*)S.quad + (size_t)(unsigned)(e0 & 3) * 32u;
+#else
   const char* p = (const char*)S.quad + (size_t)(unsigned)e0 * 32u;
+#endif
   c.q0 = ldg_quad(p);
   c.q1 = ldg_quad(p + (z1 - z0) * 128);
 }
 
-// returns dist and the three gradient components (unscaled by 1/res); xlow/ylow/out-of-map handled
+// returns dist and the three gradient components (unscaled by 1/res).  The border cases (xlow / ylow /
+// out of map) are patched behind one branch that is almost never taken.  kWarpUniform: the caller
+// guarantees that all 32 lanes reach this call together (then the branch is made warp-uniform with a
+// vote); otherwise every lane decides for itself.
+template <bool kWarpUniform>
 __device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, double& gx, double& gy, double& gz) {
+  double dx = c.dx, dy = c.dy;
+  const bool any_special = kWarpUniform ? __any_sync(kFull, c.special) : c.special;
+  if (any_special) {
+    dx = c.xlow ? 0.0 : dx;
+    dy = c.ylow ? 0.0 : dy;
+  }
   // x-lerps; the x-differences feed grad x
   const double e00 = c.q0.v10 - c.q0.v00, e10 = c.q0.v11 - c.q0.v01;  // (y0,z0), (y1,z0)
   const double e01 = c.q1.v10 - c.q1.v00, e11 = c.q1.v11 - c.q1.v01;  // (y0,z1), (y1,z1)
-  const double v00 = fma(c.dx, e00, c.q0.v00), v10 = fma(c.dx, e10, c.q0.v01);
-  const double v01 = fma(c.dx, e01, c.q1.v00), v11 = fma(c.dx, e11, c.q1.v01);
+  const double v00 = fma(dx, e00, c.q0.v00), v10 = fma(dx, e10, c.q0.v01);
+  const double v01 = fma(dx, e01, c.q1.v00), v11 = fma(dx, e11, c.q1.v01);
   // y-lerps; y-differences feed grad y
   const double f0 = v10 - v00, f1 = v11 - v01;
-  const double v0 = fma(c.dy, f0, v00), v1 = fma(c.dy, f1, v01);
-  const double h = v1 - v0;
-  const double d = fma(c.dz, h, v0);                      // :229
-  const double y = fma(c.dz, f1 - f0, f0);                // :232-233
-  const double ex0 = fma(c.dy, e10 - e00, e00), ex1 = fma(c.dy, e11 - e01, e01);
-  const double x = fma(c.dz, ex1 - ex0, ex0);             // :234-239
-  dist = c.in_map ? d : -1.0;                             // :187, H3
-  gx = (c.in_map && !c.xlow) ? x : 0.0;
-  gy = (c.in_map && !c.ylow) ? y : 0.0;
-  gz = c.in_map ? h : 0.0;                                // :231
+  const double v0 = fma(dy, f0, v00), v1 = fma(dy, f1, v01);
+  gz = v1 - v0;                                           // :231
+  dist = fma(c.dz, gz, v0);                               // :229
+  gy = fma(c.dz, f1 - f0, f0);                            // :232-233
+  const double ex0 = fma(dy, e10 - e00, e00), ex1 = fma(dy, e11 - e01, e01);
+  gx = fma(c.dz, ex1 - ex0, ex0);                         // :234-239
+  if (any_special) {
+    dist = c.in_map ? dist : -1.0;                        // :187, H3
+    gx = (c.in_map && !c.xlow) ? gx : 0.0;
+    gy = (c.in_map && !c.ylow) ? gy : 0.0;
+    gz = c.in_map ? gz : 0.0;
+  }
 }
 
 }  // namespace gtop

@@ -178,16 +178,16 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
           va = __dadd_rn(va, __dmul_rn(e[3], t4));
           vel[a] = f32_round_trip(va);
         }
-        const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], vel[0] * vel[0]));
-        const double vnorm = sqrt_pos(fmax(vn2, 1e-300)) + 1e-5;  // :358 (sqrt(1e-300) is absorbed by 1e-5)
+        const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], fma(vel[0], vel[0], 1e-300)));
+        const double vnorm = sqrt_pos(vn2) + 1e-5;  // :358 (the 1e-300 keeps v = 0 finite; absorbed by 1e-5)
         const double inv_vn = rcp_pos(vnorm);
 
         double dist, g[3];
-        sdf_finish(cell, dist, g[0], g[1], g[2]);
+        sdf_finish<false>(cell, dist, g[0], g[1], g[2]);  // lane-dependent trip count: no votes here
         oob += cell.in_map ? 0u : 1u;
 
-        // exp(-(d-d0)/r) (:509/:514) = 2^((d0-d)*log2(e)/r); d <= 10000 so clamp the exponent at -1000
-        const double ee = exp2_tab(fmax(fma(dist, E.neg_log2e_over_r, E.d0_log2e_over_r), -1000.0), xtab);
+        // exp(-(d-d0)/r) (:509/:514) = 2^((d0-d)*log2(e)/r)
+        const double ee = exp2_tab(fma(dist, E.neg_log2e_over_r, E.d0_log2e_over_r), xtab);
         const double ev = ee * vnorm;
         v[18] += ev;                       // cost: cd*|v| = alpha*ee*vnorm (alpha, dt applied later)
         // sA_a = gd*grad_a*cd*|v| = kA * ee^2 * vnorm * g_a      (:378, extra cd reproduced — H4)

@@ -29,6 +29,11 @@
 //     segments that touch it and are written once.
 //   * Coefficients c = L d (:253-279) stay scalar, in the reference's summation order, unfused.
 //   * SDF corners come from the patch-ordered xy-quad copy of the grid: 2 x LDG.256 per sample.
+//   * One 64-byte table record per (problem, segment, sample) feeds both the polynomial evaluation and
+//     the B fragments; the record of the NEXT iteration is requested as soon as the current one is dead
+//     (after the velocity polynomial), so its L2 latency hides behind the second half of the iteration.
+//   * The smoothness cost is accumulated from the gradient rows (d_u * (R d)_u) while they are formed;
+//     only the six fixed rows are left to the tail.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -38,10 +43,15 @@
 
 namespace gtop {
 
+// resident CTAs per SM asked of the compiler (register cap = 65536 / (32 * warps * MINB))
 #ifndef GTOP_MMA_MINB
-#define GTOP_MMA_MINB 5
+#define GTOP_MMA_MINB 20
 #endif
-constexpr int kMmaMaxWarps = 4;
+// one warp per CTA: the kernel has no block-level cooperation, and small CTAs pack SMs evenly
+#ifndef GTOP_MMA_WARPS
+#define GTOP_MMA_WARPS 1
+#endif
+constexpr int kMmaMaxWarps = GTOP_MMA_WARPS;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -50,8 +60,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // per-warp shared memory, in doubles:
 //   Wd   [8][wstride]   boundary derivatives per trajectory, [3][nrow] in waypoint order (nrow = 3(m+1));
 //                       wstride odd -> the 8 trajectories of a warp sit in distinct banks
-//   coef [15][8][2]     coefficient pairs of the current segment, 16-byte element per trajectory:
-//                       per axis (c0,c1) (c2,c3) (c4,c5) (2c2,3c3) (4c4,5c5)
+//   coef [8][15][2]     coefficient pairs of the current segment, 15 16-byte elements per trajectory:
+//                       per axis (c0,c1) (c2,c3) (c4,c5) (2c2,3c3) (4c4,5c5).  The 240-byte trajectory
+//                       stride puts the 8 trajectories of a warp in the 8 distinct 16-byte bank groups
+//                       both for the loads (fixed element) and the stores (element varies with the lane)
 //   scr  [8][9]         finished collision-gradient rows of one waypoint (3 axes x p,v,a)
 __host__ __device__ inline int mma_wstride(int m) { return (9 * (m + 1)) | 1; }
 __host__ __device__ inline int mma_warp_smem_doubles(int m) { return 8 * mma_wstride(m) + 240 + 72; }
@@ -61,7 +73,7 @@ __host__ __device__ inline int mma_warp_smem_doubles(int m) { return 8 * mma_wst
 // of d) with unfused mul/add — the same 6-term sum as `L * d` (:273).  Work item = (axis, power pair).
 template <bool kLast>
 __device__ __forceinline__ void coef_phase(const double* __restrict__ Wd, int nrow, int s,
-                                           const double2* __restrict__ LiTP, double2* __restrict__ coef, int g, int j) {
+                                           const double2* __restrict__ LiTP, double2* __restrict__ coef, int j) {
   for (int item = j; item < 9; item += 4) {
     const int a = item / 3, p = item - 3 * a;
     const double* w0 = Wd + a * nrow + 3 * s;  // p0,v0,a0,pT,vT,aT contiguous in waypoint order
@@ -69,7 +81,7 @@ __device__ __forceinline__ void coef_phase(const double* __restrict__ Wd, int nr
     double q0[6], q1[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      const double2 L = __ldg(wt + r);
+      const double2 L = ldg_tab(wt + r);
       const double w = w0[r];
       q0[r] = __dmul_rn(L.x, w), q1[r] = __dmul_rn(L.y, w);
     }
@@ -81,10 +93,9 @@ __device__ __forceinline__ void coef_phase(const double* __restrict__ Wd, int nr
       c0 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(q0[0], q0[1]), q0[2]), q0[3]), q0[4]), q0[5]);
       c1 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(q1[0], q1[1]), q1[2]), q1[3]), q1[4]), q1[5]);
     }
-    coef[(a * 5 + p) * 8 + g] = make_double2(c0, c1);
+    coef[a * 5 + p] = make_double2(c0, c1);
     // e_k = k*c_k for the velocity polynomial (2*coeff(s,2), 3*coeff(s,3), ... :477-485)
-    if (p >= 1)
-      coef[(a * 5 + 2 + p) * 8 + g] = make_double2(__dmul_rn((double)(2 * p), c0), __dmul_rn((double)(2 * p + 1), c1));
+    if (p >= 1) coef[a * 5 + 2 + p] = make_double2(__dmul_rn((double)(2 * p), c0), __dmul_rn((double)(2 * p + 1), c1));
   }
 }
 
@@ -114,7 +125,7 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
 
   double* wbase = smem + warp * per_warp;
   double* Wd = wbase + g * wstride;
-  double2* coef = reinterpret_cast<double2*>(wbase + 8 * wstride);
+  double2* coef = reinterpret_cast<double2*>(wbase + 8 * wstride) + g * 15;  // this trajectory's 15 pairs
   double* scr = wbase + 8 * wstride + 240 + g * 9;
 
   // all 8 trajectories of the group belong to one problem (host-checked: starts_per_problem % 8 == 0)
@@ -132,8 +143,14 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   }
   __syncwarp();
 
+  // lane constants of the B fragments: column g of the accumulation tiles carries power pw = power_of_col(g);
+  // tau_pw = slot[pw], tau'_pw = pw * slot[pw-1] (slot[6] = slot[7] = 0 serve the out-of-range cases)
+  const int pw = power_of_col(g);
+  const int offA = pw, offB = (pw >= 1 && pw < 6) ? pw - 1 : 7;
+  const double mulB = (pw >= 1 && pw < 6) ? (double)pw : 0.0;
+
   double G[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // back-projected gradient rows (C fragments)
-  double Jc = 0.0;
+  double Jc = 0.0, js = 0.0;
   unsigned oob = 0;
   const double kA = -E.alpha * E.alpha_over_r * S.res_inv;  // gd*cd = -(alpha^2/r) e^2; grad scale 1/res
   double* __restrict__ gout = grad_out + b * n;
@@ -141,26 +158,31 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   for (int s = 0; s < m; ++s) {
     if (!E.skip_collision) {
       const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + s * 36);
-      if (s == m - 1) coef_phase<true>(Wd, nrow, s, LiTP, coef, g, j);
-      else coef_phase<false>(Wd, nrow, s, LiTP, coef, g, j);
+      if (s == m - 1) coef_phase<true>(Wd, nrow, s, LiTP, coef, j);
+      else coef_phase<false>(Wd, nrow, s, LiTP, coef, j);
       __syncwarp();
 
       const int ns = (int)pr[PL.off_ns + s];
       const int nit = (ns + 3) >> 2;
-      const double2* __restrict__ T6 = reinterpret_cast<const double2*>(pr + PL.off_T6 + (s * PL.nsp + j) * 6);
-      const double2* __restrict__ BF = reinterpret_cast<const double2*>(pr + PL.off_BF + s * PL.nsp * 16 + lane * 2);
+      // this lane's 64-byte table record of the current iteration; advanced by 4 slots per iteration
+      const double* __restrict__ tp = pr + PL.off_T8 + (size_t)(s * PL.nsp + j) * 8;
+      double2 ta, tb, tc;  // (1,t) (t2,t3) (t4,t5) of the current sample, requested one iteration ahead
+      if (nit > 0) {
+        ta = ldg_tab(reinterpret_cast<const double2*>(tp));
+        tb = ldg_tab(reinterpret_cast<const double2*>(tp) + 1);
+        tc = ldg_tab(reinterpret_cast<const double2*>(tp) + 2);
+      }
 
       double U[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // moment accumulators (C fragments)
       double jseg = 0.0;
-      for (int it = 0; it < nit; ++it) {
-        const double2 ta = __ldg(T6 + it * 12), tb = __ldg(T6 + it * 12 + 1), tc = __ldg(T6 + it * 12 + 2);
-        const double2 bf = __ldg(BF + it * 32);
-        const double t = ta.x, t2 = ta.y, t3 = tb.x, t4 = tb.y, t5 = tc.x, w = tc.y;
+      for (int it = 0; it < nit; ++it, tp += 32) {
+        const double t = ta.y, t2 = tb.x, t3 = tb.y, t4 = tc.x, t5 = tc.y;
         double pos[3], vel[3], c1[3];
         float pf[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          const double2 c01 = coef[(a * 5 + 0) * 8 + g], c23 = coef[(a * 5 + 1) * 8 + g], c45 = coef[(a * 5 + 2) * 8 + g];
+          const double2 c01 = coef[a * 5 + 0], c23 = coef[a * 5 + 1], c45 = coef[a * 5 + 2];
+          c1[a] = c01.y;
           // getPositionFromCoeff (:457-465): left-to-right, unfused, then float
           double pa = __dadd_rn(c01.x, __dmul_rn(c01.y, t));
           pa = __dadd_rn(pa, __dmul_rn(c23.x, t2));
@@ -169,13 +191,12 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
           pa = __dadd_rn(pa, __dmul_rn(c45.y, t5));
           pf[a] = __double2float_rn(pa);
           pos[a] = (double)pf[a];
-          c1[a] = c01.y;
         }
         SdfCell cell;
         sdf_gather(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          const double2 e01 = coef[(a * 5 + 3) * 8 + g], e23 = coef[(a * 5 + 4) * 8 + g];
+          const double2 e01 = coef[a * 5 + 3], e23 = coef[a * 5 + 4];
           // getVelocityFromCoeff (:477-485)
           double va = __dadd_rn(c1[a], __dmul_rn(e01.x, t));
           va = __dadd_rn(va, __dmul_rn(e01.y, t2));
@@ -183,27 +204,35 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
           va = __dadd_rn(va, __dmul_rn(e23.y, t4));
           vel[a] = f32_round_trip(va);
         }
-        const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], vel[0] * vel[0]));
-        const double vnorm = sqrt_pos(fmax(vn2, 1e-300)) + 1e-5;  // :358 (sqrt(1e-300) is absorbed by 1e-5)
+        // B fragments of this sample (same 64-byte record: L1 hits), then the record of the next sample
+        const double bA = __ldg(tp + offA), bB = mulB * __ldg(tp + offB);
+        if (it + 1 < nit) {
+          ta = ldg_tab(reinterpret_cast<const double2*>(tp + 32));
+          tb = ldg_tab(reinterpret_cast<const double2*>(tp + 32) + 1);
+          tc = ldg_tab(reinterpret_cast<const double2*>(tp + 32) + 2);
+        }
+
+        const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], fma(vel[0], vel[0], 1e-300)));
+        const double vnorm = sqrt_pos(vn2) + 1e-5;  // :358 (the 1e-300 keeps v = 0 finite; absorbed by 1e-5)
         const double inv_vn = rcp_pos(vnorm);
 
         double dist, gd[3];
-        sdf_finish(cell, dist, gd[0], gd[1], gd[2]);
-        oob += (!cell.in_map && 4 * it + j < ns) ? 1u : 0u;
+        sdf_finish<true>(cell, dist, gd[0], gd[1], gd[2]);  // the sample loop is warp-uniform
+        const bool real = 4 * it + j < ns;  // padding slots evaluate the segment start with zero weights
+        oob += (!cell.in_map && real) ? 1u : 0u;
 
-        // exp(-(d-d0)/r) (:509/:514) = 2^((d0-d)*log2(e)/r); d <= 10000 so clamp the exponent
-        const double ee =
-            exp2_tab(fmin(fmax(fma(dist, E.neg_log2e_over_r, E.d0_log2e_over_r), -1000.0), 1000.0), xtab);
+        // exp(-(d-d0)/r) (:509/:514) = 2^((d0-d)*log2(e)/r)
+        const double ee = exp2_tab(fma(dist, E.neg_log2e_over_r, E.d0_log2e_over_r), xtab);
         const double ev = ee * vnorm;
-        jseg = fma(w, ev, jseg);           // cost: cd*|v| = alpha*ee*vnorm (alpha, dt applied later)
+        jseg += real ? ev : 0.0;           // cost: cd*|v| = alpha*ee*vnorm (alpha, dt applied later)
         // sA_a = gd*grad_a*cd*|v| = kA * ee^2 * vnorm * g_a      (:378, extra cd reproduced — H4)
         // sB_a = cd*v_a/|v|       = alpha * ee * v_a / vnorm     (:379)
         const double sAc = kA * (ee * ev);
         const double sBc = E.alpha * (ee * inv_vn);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          dmma884(U[a][0], U[a][1], sAc * gd[a], bf.x);   // += sA_a(sample) * tau_i(sample)
-          dmma884(U[a][0], U[a][1], sBc * vel[a], bf.y);  // += sB_a(sample) * tau'_i(sample)
+          dmma884(U[a][0], U[a][1], sAc * gd[a], bA);   // += sA_a(sample) * tau_i(sample)
+          dmma884(U[a][0], U[a][1], sBc * vel[a], bB);  // += sB_a(sample) * tau'_i(sample)
         }
       }
       Jc = fma(jseg, pr[PL.off_dt + s], Jc);
@@ -232,7 +261,8 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
     __syncwarp();
     if (s >= 1) {
       // smoothness rows 2 Rfp' df + 2 Rpp dp (:330-332) from the band of R, combined with the collision
-      // rows and written out (:425-431): 9 values per trajectory over its 4 lanes
+      // rows and written out (:425-431): 9 values per trajectory over its 4 lanes.  The same row
+      // products give the interior rows of the smoothness cost d' R d (:326-327).
       for (int o = j; o < 9; o += 4) {
         const int a = o / 3, r = o - 3 * a, jj = 3 * (s - 1) + r;
         const double* __restrict__ band = pr + PL.off_Rg + jj * 9;
@@ -240,6 +270,7 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
         double gs = 0.0;
 #pragma unroll
         for (int u = 0; u < 9; ++u) gs = fma(Wb[u], band[u], gs);
+        js = fma(gs, Wb[3 + r], js);
         const double val = (E.ws * (2.0 * gs) + E.wc * scr[o]) + 1e-5;
         if (live) gout[a * P + jj] = val;
       }
@@ -251,12 +282,12 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
     if (lane == 0 && oob) atomicAdd(oob_counter, (unsigned long long)oob);
   }
 
-  // ---- smoothness cost: banded column sums of R in waypoint order (:326-327) -----------------------
-  double js = 0.0;
-  for (int u = j; u < nrow; u += 4) {
+  // ---- smoothness cost, fixed rows (first and last waypoint): column band of R (:326-327) -----------
+  for (int o = j; o < 6; o += 4) {
+    const int u = o < 3 ? o : 3 * m + (o - 3);
     const double* __restrict__ band = pr + PL.off_Rc + u * 9;
-    const int base = 3 * (u / 3 - 1);
-    const int j0 = base < 0 ? 3 : 0, j1 = (base + 9 > nrow) ? 6 : 9;
+    const int base = o < 3 ? -3 : 3 * m - 3;
+    const int j0 = o < 3 ? 3 : 0, j1 = o < 3 ? 9 : 6;
     double y0 = 0.0, y1 = 0.0, y2 = 0.0;
     for (int jj = j0; jj < j1; ++jj) {
       const double bv = band[jj];

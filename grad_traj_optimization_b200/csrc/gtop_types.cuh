@@ -55,11 +55,11 @@ inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 
 //   LinvT [m][6][6]      transpose of Linv (col = power): the coefficient step reads 6 contiguous
 //                        doubles per derivative instead of a stride-6 column
 // Sections read by the multi-start kernel k_eval_mma (eval_mma_kernel.cu); nsp = ns_cap rounded up to 4:
-//   T6    [m][nsp][6]    per sample slot (t, t^2, t^3, t^4, t^5, w): w = 1 for a real sample, 0 for a
-//                        padding slot (which repeats the last real sample's times)
-//   BF    [m][nsp/4][32][2]  B fragments of the accumulation DMMAs: lane 4g+j of iteration `it` holds
-//                        (tau, tau') of sample 4*it+j for power kPowerOfCol[g]  (tau_i = t^i,
-//                        tau'_i = i t^(i-1), :379; zeros for padding slots and powers 6,7)
+//   T8    [m][nsp][8]    per sample slot (1, t, t^2, t^3, t^4, t^5, 0, 0) — one 64-byte record serves the
+//                        polynomial evaluation (t..t^5) AND, read at a lane-dependent offset, the B
+//                        fragments of the accumulation DMMAs (tau_i = t^i, tau'_i = i t^(i-1), :379).
+//                        Padding slots (k >= ns) are all zero: they evaluate the segment's start point and
+//                        contribute nothing.
 //   LB    [m][2][32]     B fragments of the back-projection DMMAs: dt_s * Linv_s[4*ks + j][r(g)], where
 //                        column g <-> local derivative r alternates with the segment parity so that the
 //                        end-derivative columns of segment s are the start-derivative columns of s+1
@@ -71,7 +71,7 @@ struct ProbLayout {
   int ns_cap;  // samples_per_segment (table capacity)
   int nsp;     // ns_cap rounded up to a multiple of 4
   int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df, off_LinvT;
-  int off_T6, off_BF, off_LB, off_LiTP;
+  int off_T8, off_LB, off_LiTP;
   int stride;
 };
 
@@ -99,11 +99,11 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   L.off_LinvT = o, o += m * 36;
   o = (o + 1) & ~1;
   L.nsp = (ns_cap + 3) & ~3;
-  L.off_T6 = o, o += m * L.nsp * 6;
-  L.off_BF = o, o += m * L.nsp * 16;
+  o = (o + 7) & ~7;  // 64-byte aligned slots (relative to the 16-byte aligned record)
+  L.off_T8 = o, o += m * L.nsp * 8;
   L.off_LB = o, o += m * 64;
   L.off_LiTP = o, o += m * 36;
-  L.stride = (o + 1) & ~1;  // keep every record 16-byte aligned
+  L.stride = (o + 7) & ~7;  // keep every record 64-byte aligned
   return L;
 }
 

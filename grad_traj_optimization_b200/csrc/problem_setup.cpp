@@ -295,19 +295,10 @@ void pack_record(const ProblemHost& p, double* rec) {
     const double* tt = &p.tt[(size_t)s * 5 * NS];
     const int ns = (int)p.ns[s];
     for (int k = 0; k < NSP; ++k) {
-      const int ks = ns > 0 ? (k < ns ? k : ns - 1) : -1;  // padding slots repeat the last real sample
-      double pw[8] = {1.0, 0, 0, 0, 0, 0, 0, 0};           // tau_i = t^i                  (:549)
-      for (int q = 1; q <= 5; ++q) pw[q] = ks >= 0 ? tt[(size_t)(q - 1) * NS + ks] : 0.0;
-      double* t6 = rec + L.off_T6 + ((size_t)s * NSP + k) * 6;
-      for (int q = 1; q <= 5; ++q) t6[q - 1] = pw[q];
-      t6[5] = k < ns ? 1.0 : 0.0;
-      const bool real = k < ns;
-      for (int g = 0; g < 8; ++g) {
-        const int i = power_of_col(g);
-        double* bf = rec + L.off_BF + (size_t)s * NSP * 16 + (size_t)(k >> 2) * 64 + (size_t)(4 * g + (k & 3)) * 2;
-        bf[0] = (real && i < 6) ? pw[i] : 0.0;
-        bf[1] = (real && i >= 1 && i < 6) ? (double)i * pw[i - 1] : 0.0;  // T*V: tau'_i = i t^(i-1)  (:379)
-      }
+      double* t8 = rec + L.off_T8 + ((size_t)s * NSP + k) * 8;  // zero-filled by the memset above
+      if (k >= ns) continue;                                     // padding slot: all zero
+      t8[0] = 1.0;                                               // tau_i = t^i                  (:549)
+      for (int q = 1; q <= 5; ++q) t8[q] = tt[(size_t)(q - 1) * NS + k];
     }
     for (int ks = 0; ks < 2; ++ks)
       for (int lane = 0; lane < 32; ++lane) {
