@@ -106,7 +106,8 @@ def ncu_traffic_bytes():
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("k_eval_traj_dram_bytes_per_launch")
+            d = json.load(open(p))
+            return d.get("k_eval_mma_dram_bytes_per_launch", d.get("k_eval_traj_dram_bytes_per_launch"))
         except Exception:
             return None
     return None
@@ -234,7 +235,7 @@ def run_ours(args):
                        "l2": "4 rotating X/grad buffer sets (340 MB > 126 MB L2); the 16 MB SDF grid is L2-resident by "
                              "construction", "out_of_map_samples_per_step": oob // max(1, args.steps + max(args.warmup, 3))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_bytes(), "peak_kind": peak_kind, "kernel": "k_eval_traj",
+                         "traffic": ncu_traffic_bytes(), "peak_kind": peak_kind, "kernel": "k_eval_mma",
                          "algorithmic_bytes_per_eval": bytes_eval, "kernel_ms": ms_step},
             "cpu_baseline": cpu,
             "e2e": {"value": total_evals / (e2e_ms * 1e-3 / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": B * n * 8,

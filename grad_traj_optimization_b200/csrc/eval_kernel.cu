@@ -67,6 +67,10 @@ __device__ __forceinline__ void xreduce_step(double (&v)[20], int lane, int bit)
 //   rs   [20]        the 19 reduced sums of the current segment
 __host__ __device__ inline int traj_smem_doubles(int m) { return 2 * 9 * (m + 1) + 32 + 20; }
 
+// kVelAcc: also evaluate the velocity / acceleration penalty block that upstream HEAD has commented out
+// (:383-407, penalties :517-535) — gtop_params.vel_acc_penalty, default off; literal restatement including
+// the `cv` / `ca` values carried from the k = 2 iteration of the cost loop into the gradient loop.
+template <bool kVelAcc>
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, GTOP_EVAL_MINB)
 k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_problems, EvalScalars E,
             const double* __restrict__ X, int64_t B, int64_t traj_offset, int64_t starts_per_problem,
@@ -111,7 +115,7 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
   const int red_base = 10 * ((j >> 2) & 1) + 5 * ((j >> 1) & 1) + 3 * (j & 1);
   const int red_cnt = (j & 1) ? 2 : 3;  // odd lanes hold (3,4,pad) of their group of five
 
-  double Jc_total = 0.0;
+  double Jc_total = 0.0, Jva_total = 0.0;
   unsigned oob = 0;
   const double kA = -E.alpha * E.alpha_over_r * S.res_inv;  // gd*cd = -(alpha^2/r) e^2; grad scale 1/res
   const int ns_cap = PL.ns_cap;
@@ -144,7 +148,7 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
       const double dt = pr[PL.off_dt + s];
       const double* __restrict__ tt = pr + PL.off_tt + s * 5 * ns_cap;
 
-      double v[20];  // U[a][i] at a*6+i, cost at 18, pad at 19
+      double v[20];  // U[a][i] at a*6+i, cost at 18, velocity/acceleration penalty cost at 19
 #pragma unroll
       for (int i = 0; i < 20; ++i) v[i] = 0.0;
 
@@ -195,15 +199,47 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
         const double sAc = kA * (ee * ev);
         const double sBc = E.alpha * (ee * inv_vn);
         const double tp2 = 2.0 * t, tp3 = 3.0 * t2, tp4 = 4.0 * t3, tp5 = 5.0 * t4;  // T*V (:379)
+        double sBv[3] = {0.0, 0.0, 0.0}, sCv[3] = {0.0, 0.0, 0.0};
+        if (kVelAcc) {
+          // getAccelerationFromCoeff (:491-505): 2c2 + 6c3 t + 12c4 t^2 + 20c5 t^3, left to right, then float.
+          // 6c3 = 2*(3c3), 12c4 = 3*(4c4), 20c5 = 4*(5c5) round identically from the e_k = k*c_k already held.
+          double cv[3], ca[3], gv[3], gacc[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const double* e = cb + 18 + a * 4;
+            double aa = __dadd_rn(e[0], __dmul_rn(2.0 * e[1], t));
+            aa = __dadd_rn(aa, __dmul_rn(__dmul_rn(3.0, e[2]), t2));
+            aa = __dadd_rn(aa, __dmul_rn(4.0 * e[3], t3));
+            const double acc = f32_round_trip(aa);
+            const double xv = exp2_tab(fma(fabs(vel[a]), E.log2e_over_rv, E.neg_v0_log2e_over_rv), xtab);
+            const double xa = exp2_tab(fma(fabs(acc), E.log2e_over_ra, E.neg_a0_log2e_over_ra), xtab);
+            cv[a] = E.alpha_v * xv, gv[a] = E.alpha_v_over_r * xv;    // :517-525
+            ca[a] = E.alpha_a * xa, gacc[a] = E.alpha_a_over_r * xa;  // :527-535
+          }
+          v[19] += ((cv[0] + cv[1]) + cv[2] + (ca[0] + ca[1]) + ca[2]) * vnorm;  // cost_vel + cost_acc (:388-392)
+          const double carried = (cv[2] + ca[2]) * inv_vn;  // `cv`, `ca` keep their k = 2 values in the second loop
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            // (gv*|v| + cv*v_a/|v| + ca*v_a/|v|) T V Ldp  and  ga*|v| T V V Ldp   (:396-404), weights wv = wa = 1
+            sBv[a] = E.inv_wc * fma(gv[a], vnorm, carried * vel[a]);
+            sCv[a] = E.inv_wc * (gacc[a] * vnorm);
+          }
+        }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          const double sA = sAc * g[a], sB = sBc * vel[a];
+          const double sA = sAc * g[a], sB = sBc * vel[a] + sBv[a];
           v[a * 6 + 0] += sA;
           v[a * 6 + 1] += fma(sA, t, sB);
           v[a * 6 + 2] += fma(sA, t2, sB * tp2);
           v[a * 6 + 3] += fma(sA, t3, sB * tp3);
           v[a * 6 + 4] += fma(sA, t4, sB * tp4);
           v[a * 6 + 5] += fma(sA, t5, sB * tp5);
+          if (kVelAcc) {  // T*V*V = (0, 0, 2, 6t, 12t^2, 20t^3)
+            v[a * 6 + 2] = fma(sCv[a], 2.0, v[a * 6 + 2]);
+            v[a * 6 + 3] = fma(sCv[a], 3.0 * tp2, v[a * 6 + 3]);
+            v[a * 6 + 4] = fma(sCv[a], 4.0 * tp3, v[a * 6 + 4]);
+            v[a * 6 + 5] = fma(sCv[a], 5.0 * tp4, v[a * 6 + 5]);
+          }
         }
       }
 
@@ -214,9 +250,10 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
       xreduce_step<3>(v, lane, 1);
 #pragma unroll
       for (int i = 0; i < 3; ++i)
-        if (i < red_cnt && red_base + i < 19) rs[red_base + i] = v[i];
+        if (i < red_cnt && red_base + i < 20) rs[red_base + i] = v[i];
       __syncwarp();
       Jc_total = fma(rs[18], dt, Jc_total);
+      if (kVelAcc) Jva_total = fma(rs[19], dt, Jva_total);
       // ---- back-projection through the segment block: g[a][r] = sum_i U[a][i]*Linv[i][r] (T*Ldp, :378-379)
 #pragma unroll
       for (int o = j; o < 18; o += 8) {
@@ -272,7 +309,8 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
       gout[P + jj] = (E.ws * (2.0 * g1) + E.wc * ga[nrow + 3 + jj]) + 1e-5;
       gout[2 * P + jj] = (E.ws * (2.0 * g2) + E.wc * ga[2 * nrow + 3 + jj]) + 1e-5;
     }
-    if (j == 0) cost_out[b] = E.ws * js + E.wc * (E.alpha * Jc_total) + 1e-3;
+    // wv = wa = 1 (:412)
+    if (j == 0) cost_out[b] = E.ws * js + E.wc * (E.alpha * Jc_total) + (kVelAcc ? Jva_total : 0.0) + 1e-3;
   }
 }
 
@@ -298,7 +336,7 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
                         int max_ctas, cudaStream_t stream) {
   (void)max_ctas;
   if (B <= 0) return cudaSuccess;
-  if (!force_general() && eval_mma_applicable(PL, traj_offset, starts_per_problem))
+  if (!force_general() && !E.vel_acc && eval_mma_applicable(PL, traj_offset, starts_per_problem))
     return launch_eval_mma(S, PL, prob, num_problems, E, X, B, traj_offset, starts_per_problem, cost, grad, oob_counter,
                            stream);
   // warps per CTA: as many as keep the CTA's shared memory modest (4 CTAs/SM at 16 warps/SM)
@@ -306,14 +344,15 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
   int wpc = kMaxWarpsPerCta;
   while (wpc > 1 && per_warp * wpc + 512 > 48 * 1024) wpc >>= 1;
   const size_t smem = per_warp * wpc + kExpTab * sizeof(double);
+  auto kern = E.vel_acc ? k_eval_traj<true> : k_eval_traj<false>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_eval_traj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   const int64_t per_cta = (int64_t)wpc * kTrajPerWarp;
   const int64_t grid = (B + per_cta - 1) / per_cta;
-  k_eval_traj<<<(unsigned)grid, wpc * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset,
-                                                          starts_per_problem, cost, grad, oob_counter);
+  kern<<<(unsigned)grid, wpc * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset, starts_per_problem,
+                                                   cost, grad, oob_counter);
   return cudaGetLastError();
 }
 

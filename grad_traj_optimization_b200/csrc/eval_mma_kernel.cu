@@ -37,6 +37,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "eval_common.cuh"
 #include "gtop_types.cuh"
@@ -321,7 +322,11 @@ cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double
   const size_t per_warp = sizeof(double) * (size_t)mma_warp_smem_doubles(PL.m);
   int wpc = kMmaMaxWarps;
   while (wpc > 1 && per_warp * wpc + 512 > 40 * 1024) wpc >>= 1;
-  const size_t smem = per_warp * wpc + kExpTab * sizeof(double);
+  size_t smem = per_warp * wpc + kExpTab * sizeof(double);
+  {  // tuning knob: extra dynamic shared memory per CTA limits the resident CTAs per SM
+    static const long pad = [] { const char* e = std::getenv("GTOP_MMA_SMEM_PAD"); return e ? std::atol(e) : 0L; }();
+    smem += (size_t)pad;
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_eval_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

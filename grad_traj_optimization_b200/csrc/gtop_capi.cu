@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -75,7 +76,8 @@ struct gtop_problems {
   std::vector<ProblemHost> host;
   double* rec = nullptr;               // np * layout.stride doubles
   unsigned long long* oob = nullptr;   // device counter
-  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};  // [0] compute (and default), [1] H2D, [2] D2H
+  cudaEvent_t ev_in[16] = {}, ev_done[16] = {};            // per-chunk hand-offs of gtop_eval_batch_host
   // staging for the *_host entry point (grown on demand)
   double *dX = nullptr, *dcost = nullptr, *dgrad = nullptr;
   int64_t cap = 0;
@@ -103,6 +105,13 @@ static EvalScalars make_scalars(const gtop_params& p, int step) {
   E.neg_log2e_over_r = -log2e / p.r;
   E.d0_log2e_over_r = p.d0 * log2e / p.r;
   E.skip_collision = std::fabs(p.w_collision) < 1e-4 ? 1 : 0;  // :346
+  // the optional block sits inside the sample loop, under `if (step == 2)` (:384)
+  E.vel_acc = (p.vel_acc_penalty && step == GTOP_OPT_SECOND_STEP && !E.skip_collision) ? 1 : 0;
+  E.alpha_v = p.alpha_v, E.alpha_v_over_r = p.alpha_v / p.r_v;
+  E.log2e_over_rv = log2e / p.r_v, E.neg_v0_log2e_over_rv = -p.v0 * log2e / p.r_v;
+  E.alpha_a = p.alpha_a, E.alpha_a_over_r = p.alpha_a / p.r_a;
+  E.log2e_over_ra = log2e / p.r_a, E.neg_a0_log2e_over_ra = -p.a0 * log2e / p.r_a;
+  E.inv_wc = E.skip_collision ? 0.0 : 1.0 / p.w_collision;
   return E;
 }
 
@@ -354,6 +363,10 @@ static int finish_problems(gtop_problems* p, gtop_problems** out) {
   if (e == cudaSuccess) e = cudaMalloc(&p->oob, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(p->oob, 0, sizeof(unsigned long long));
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 16 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     gtop_problems_destroy(p);
     return fail(GTOP_E_ALLOC, std::string("problem upload: ") + cudaGetErrorString(e));
@@ -366,8 +379,7 @@ static int check_params(const gtop_params* prm) {
   REQUIRE(prm, "null params");
   REQUIRE(prm->samples_per_segment >= 1 && prm->samples_per_segment <= 4096, "samples_per_segment out of range");
   REQUIRE(prm->r != 0.0, "r must be non-zero");
-  if (prm->vel_acc_penalty)
-    return fail(GTOP_E_INVALID, "vel_acc_penalty=1 (the block commented out upstream, :383-407) is not built yet");
+  if (prm->vel_acc_penalty) REQUIRE(prm->r_v != 0.0 && prm->r_a != 0.0, "r_v and r_a must be non-zero with vel_acc_penalty");
   return GTOP_OK;
 }
 
@@ -456,6 +468,10 @@ int gtop_problems_destroy(gtop_problems* p) {
   cudaFree(p->rec), cudaFree(p->oob), cudaFree(p->dX), cudaFree(p->dcost), cudaFree(p->dgrad);
   for (auto& s : p->streams)
     if (s) cudaStreamDestroy(s);
+  for (int i = 0; i < 16; ++i) {
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+  }
   delete p;
   return GTOP_OK;
 }
@@ -560,19 +576,26 @@ int gtop_eval_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, const do
     pr->cap = B;
   }
   const EvalScalars E = make_scalars(pr->prm, step);
-  // chunked 3-stream pipeline: H2D(x) | kernel | D2H(cost, grad) overlap across chunks
-  int64_t nchunk = std::min<int64_t>(12, (B + 2047) / 2048);
-  const int64_t per = (B + nchunk - 1) / nchunk;
+  // chunked pipeline over three streams: all H2D copies of x back to back on the copy-in stream, the kernels
+  // on the compute stream as their chunk lands, cost/gradient copied out on the copy-out stream as each
+  // kernel finishes (the two PCIe directions and the SMs are busy at the same time)
+  static const int64_t max_chunks = [] { const char* e = std::getenv("GTOP_HOST_CHUNKS"); return e ? std::max(1L, std::min(16L, std::atol(e))) : 8L; }();
+  const int64_t nchunk = std::min<int64_t>(max_chunks, (B + 4095) / 4096);
+  const int64_t per = ((B + nchunk - 1) / nchunk + 63) & ~int64_t(63);  // whole lane groups per chunk
+  cudaStream_t s_k = pr->streams[0], s_in = pr->streams[1], s_out = pr->streams[2];
   for (int64_t c = 0; c < nchunk; ++c) {
     const int64_t b0 = c * per, bn = std::min(per, B - b0);
     if (bn <= 0) break;
-    cudaStream_t st = pr->streams[c % 3];
-    CU(cudaMemcpyAsync(pr->dX + b0 * n, X + b0 * n, sizeof(double) * bn * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(pr->dX + b0 * n, X + b0 * n, sizeof(double) * bn * n, cudaMemcpyHostToDevice, s_in));
+    CU(cudaEventRecord(pr->ev_in[c], s_in));
+    CU(cudaStreamWaitEvent(s_k, pr->ev_in[c], 0));
     CU(launch_eval(sdf->view, pr->layout, pr->rec, pr->np, E, pr->dX + b0 * n, bn, off + b0, starts, pr->dcost + b0,
-                   pr->dgrad + b0 * n, pr->oob, 0, st));
+                   pr->dgrad + b0 * n, pr->oob, 0, s_k));
     ++g_launches;
-    CU(cudaMemcpyAsync(grad + b0 * n, pr->dgrad + b0 * n, sizeof(double) * bn * n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(cost + b0, pr->dcost + b0, sizeof(double) * bn, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(pr->ev_done[c], s_k));
+    CU(cudaStreamWaitEvent(s_out, pr->ev_done[c], 0));
+    CU(cudaMemcpyAsync(grad + b0 * n, pr->dgrad + b0 * n, sizeof(double) * bn * n, cudaMemcpyDeviceToHost, s_out));
+    CU(cudaMemcpyAsync(cost + b0, pr->dcost + b0, sizeof(double) * bn, cudaMemcpyDeviceToHost, s_out));
   }
   for (auto& st : pr->streams) CU(cudaStreamSynchronize(st));
   if (n_oob) return gtop_problems_take_out_of_map(pr, n_oob);

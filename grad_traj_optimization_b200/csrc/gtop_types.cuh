@@ -116,6 +116,12 @@ struct EvalScalars {
   double neg_log2e_over_r;  // -log2(e)/r      } exp(-(d-d0)/r) = 2^(d*neg_log2e_over_r + d0_log2e_over_r)
   double d0_log2e_over_r;   // d0*log2(e)/r    }
   int skip_collision;     // |wc| < 1e-4 (:346)
+  // optional velocity / acceleration penalties (the block commented out upstream, :383-407, :517-535);
+  // vel_acc != 0 only when gtop_params.vel_acc_penalty is set and step == OPT_SECOND_STEP
+  int vel_acc;
+  double alpha_v, alpha_v_over_r, log2e_over_rv, neg_v0_log2e_over_rv;  // cv = alpha_v * 2^(|v|*k + c)
+  double alpha_a, alpha_a_over_r, log2e_over_ra, neg_a0_log2e_over_ra;
+  double inv_wc;          // 1/wc: the penalty gradients (weight 1) ride in the collision accumulators (weight wc)
 };
 
 }  // namespace gtop

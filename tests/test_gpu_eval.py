@@ -189,3 +189,83 @@ def test_golden_vectors(gtop_lib):
             c, g, _ = ps.eval_host(gm, X, step=step, starts_per_problem=X.shape[0])
             assert rel_cost_err(c, gold["%s_cost_step%d" % (name, step)]).max() <= TOL
             assert rel_grad_err(g, gold["%s_grad_step%d" % (name, step)]).max() <= TOL
+
+
+def test_both_kernels_agree_on_one_problem(gtop_lib):
+    """The same batch through the multi-start DMMA kernel (starts_per_problem % 8 == 0) and through the general
+    quarter-warp kernel (any other value; with a single problem the mapping does not change) agrees to rounding
+    and both meet the parity gate.  Ragged sizes: B = 37 is neither a multiple of 8 nor of 4."""
+    api = _api()
+    cfg = fx.load_cfg("opti_node")
+    om = oracle_map_from_cfg(cfg)
+    opt = oracle_problem(cfg, om, cfg["waypoints"])
+    gm = _gpu_map_from_oracle(om)
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+    X = _starts(opt, 37, seed=11)
+    for step in (1, 2):
+        c_ref, g_ref, _, _ = opt.eval_batch(X, step)
+        c_m, g_m, _ = ps.eval_host(gm, X, step=step, starts_per_problem=8)   # k_eval_mma
+        c_g, g_g, _ = ps.eval_host(gm, X, step=step, starts_per_problem=37)  # k_eval_traj
+        for c, g in ((c_m, g_m), (c_g, g_g)):
+            assert rel_cost_err(c, c_ref).max() <= TOL and rel_grad_err(g, g_ref).max() <= TOL
+        assert rel_cost_err(c_m, c_g).max() <= 1e-12 and rel_grad_err(g_m, g_g).max() <= 1e-12
+    # an offset that is not a multiple of 8 keeps the lane groups aligned on the global index: bit-identical rows
+    c_all, g_all, _ = ps.eval_host(gm, X, step=2, starts_per_problem=8)
+    c_off, g_off, _ = ps.eval_host(gm, X[5:29], step=2, traj_offset=5, starts_per_problem=8)
+    assert np.array_equal(c_off, c_all[5:29]) and np.array_equal(g_off, g_all[5:29])
+
+
+@pytest.mark.parametrize("starts", [8, 5])  # DMMA kernel / general kernel
+def test_map_border_cells_follow_the_clamped_corner_rule(gtop_lib, starts):
+    """Samples within half a voxel of the lower map faces have cell index -1 on that axis and the reference
+    clamps both corners to voxel 0 (getDistance(Vector3i), sdf_map.cpp:166-174); samples next to the upper
+    faces clamp to the last voxel.  The quad-layout gather handles these through its xlow / ylow path."""
+    api = _api()
+    origin, res, size = np.array([-2.0, -1.5, 0.0]), 0.1, np.array([4.0, 3.0, 2.0])
+    from oracle import OracleMap
+    om = OracleMap(origin, res, size)
+    om.reset()
+    rng = fx.Rng(99)
+    pts = origin + rng.uniform((400, 3)) * size
+    om.set_occupancy(pts[(np.abs(pts[:, 1]) > 0.6) | (pts[:, 2] > 1.2)])  # keep a corridor around y = 0 partly free
+    om.update_esdf()
+    gm = _gpu_map_from_oracle(om)
+    prm = dict(fx.PARAMS_OPTI, bos=0.02, vos=0.05, aos=0.05)  # starts stay next to the straight lines below
+    paths = [
+        [[-1.9, -1.47, 0.03], [-0.6, -1.48, 0.02], [0.7, -1.46, 0.04], [1.9, -1.47, 0.03]],   # low y, low z faces
+        [[-1.97, -1.2, 1.0], [-1.98, -0.2, 1.0], [-1.96, 0.6, 1.0], [-1.97, 1.4, 1.0]],       # low x face
+        [[1.96, -1.3, 1.97], [1.97, -0.3, 1.96], [1.98, 0.5, 1.97], [1.97, 1.46, 1.98]],      # upper x, z (and y) faces
+    ]
+    for wp in paths:
+        wp = np.asarray(wp)
+        opt = oracle_problem(prm, om, wp)
+        ps = api.ProblemSet.from_paths(wp, api.make_params(prm))
+        X = _starts(opt, starts, seed=4)
+        c_ref, g_ref, oob_ref, _ = opt.eval_batch(X, 2)
+        c, g, oob = ps.eval_host(gm, X, step=2, starts_per_problem=starts)
+        assert oob == oob_ref
+        assert rel_cost_err(c, c_ref).max() <= TOL and rel_grad_err(g, g_ref).max() <= TOL
+
+
+@pytest.mark.parametrize("starts", [16, 5])
+def test_velocity_acceleration_penalty_flag(gtop_lib, starts):
+    """the velocity / acceleration penalty block that upstream HEAD has commented out
+    (grad_traj_optimizer.cpp:383-407, penalties :517-535) behind gtop_params.vel_acc_penalty (default off).
+    Literal restatement on both sides (cv / ca carried from the k = 2 iteration, no sign(v)); step 2 only.
+    Parity is unpinned upstream; the gate is the same 1e-9 against the oracle's restatement."""
+    api = _api()
+    cfg = fx.load_cfg("opti_node")
+    om = oracle_map_from_cfg(cfg)
+    prm = dict(cfg["params"], alpha_v=2.0, v0=1.5, r_v=0.8, alpha_a=1.5, a0=2.0, r_a=1.2, vel_acc_penalty=1)
+    opt = oracle_problem(prm, om, cfg["waypoints"])
+    gm = _gpu_map_from_oracle(om)
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(prm))
+    X = _starts(opt, starts, seed=21)
+    base = oracle_problem(dict(prm, vel_acc_penalty=0), om, cfg["waypoints"])
+    for step in (1, 2):
+        c_ref, g_ref, _, _ = opt.eval_batch(X, step)
+        c, g, _ = ps.eval_host(gm, X, step=step, starts_per_problem=starts)
+        assert rel_cost_err(c, c_ref).max() <= TOL and rel_grad_err(g, g_ref).max() <= TOL
+        c_off, _, _, _ = base.eval_batch(X, step)
+        # the block only acts in OPT_SECOND_STEP, and there it must change the objective noticeably
+        assert (np.abs(c_ref - c_off).max() > 1e-3 * np.abs(c_off).max()) == (step == 2)
