@@ -201,6 +201,7 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
   v.dist = s->dist;
   v.quad = s->quad;
   CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));  // sdf_map.cpp:22-23
+  s->dist_fresh = true;
   CU(launch_build_quads(v, s->dist, s->quad, s->stream));
   g_launches += 2;
   CU(cudaStreamSynchronize(s->stream));
@@ -229,6 +230,7 @@ int gtop_sdf_reset(gtop_sdf* s) {
   REQUIRE(s, "null sdf");
   CU(cudaSetDevice(s->device));
   CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));
+  s->dist_fresh = true;
   CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   g_launches += 2;
   CU(cudaStreamSynchronize(s->stream));
@@ -300,6 +302,7 @@ int gtop_sdf_upload_distance(gtop_sdf* s, const double* host) {
   REQUIRE(s && host, "null argument");
   CU(cudaSetDevice(s->device));
   CU(cudaMemcpy(s->dist, host, sizeof(double) * s->nvox, cudaMemcpyHostToDevice));
+  s->dist_fresh = false;
   CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   ++g_launches;
   CU(cudaStreamSynchronize(s->stream));

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "gtop_types.cuh"
 
@@ -137,18 +138,23 @@ k_edt_z(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t ncol
 // ---------------------------------------------------------------------------------------------
 // 1-D lower envelope of parabolas on one strided row, exact integer arithmetic.
 //   out[u] = min_i ( (u-i)^2 + g[i] ),   g[i] in [0, kInf]  (kInf = +inf)
-// Stack of (site, first index where the site wins) kept in local memory (16-bit entries: rows are
-// < 32768 long).  F(x,i) = (x-i)^2 + g(i).
+// Stack of (site, first index where the site wins, g(site)) packed in ONE 8-byte local-memory entry
+// per level (rows are < 32768 long: 16-bit site and start), with the top entry held in registers: a
+// push is one 8-byte store, a pop one 8-byte load, the common "compare with the top" touches no memory.
+// (Three separate arrays cost three uncoalesced local accesses per step: the x pass of the 2000x2000x400
+// map moved 184 GB through L1/L2 for 19 GB of useful traffic.)  F(x,i) = (x-i)^2 + g(i).
+// Rows up to 8192 long keep every intermediate below 2^31 (u^2 + 3 n^2 <= 2.7e8), so the intersection
+// is a 32-bit division; longer rows use 64-bit arithmetic.
 template <int MAXN, bool FINAL>
 __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int64_t gstride, int n,
                                              int32_t* __restrict__ out_i, double* __restrict__ out_d, double res,
                                              bool fresh) {
-  short s[MAXN];  // sites
-  short t[MAXN];  // t[q]: first x at which site s[q] is the minimiser
-  int gs[MAXN];   // g(s[q]) cached next to the stack (avoids a dependent strided re-load)
-  int q = -1;
+  typedef typename std::conditional<(MAXN <= 8192), int, long long>::type wide_t;
+  int2 st[MAXN];  // st[q] = (site | start << 16, g(site)) for q below the top
+  int q = -1;     // index of the top entry (kept in ts / tt / tg)
+  int ts = 0, tt = 0, tg = 0;
   // The row loads do not depend on the stack: fetch them kPF elements ahead so that several strided
-  // (and, in the x pass, TLB-missing) loads are in flight while the envelope logic runs.
+  // loads are in flight while the envelope logic runs.
   constexpr int kPF = 8;
   int gbuf[kPF];
 #pragma unroll
@@ -167,18 +173,26 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
       if (gu >= kInf) continue;  // an infinite parabola never wins (also pads past the row end)
       // pop while the new parabola is below the top one at the top's start
       while (q >= 0) {
-        const int x = t[q], dq = x - s[q], du = x - u;
-        if ((long long)dq * dq + gs[q] > (long long)du * du + gu) --q;
-        else break;
+        const int dq = tt - ts, du = tt - u;
+        if ((wide_t)dq * dq + tg > (wide_t)du * du + gu) {
+          if (--q >= 0) {
+            const int2 e = st[q];
+            ts = e.x & 0xffff, tt = (unsigned)e.x >> 16, tg = e.y;
+          }
+        } else {
+          break;
+        }
       }
       if (q < 0) {
-        q = 0, s[0] = (short)u, t[0] = 0, gs[0] = gu;
+        q = 0, ts = u, tt = 0, tg = gu;
       } else {
         // Sep(i,u) = floor((u^2 - i^2 + g(u) - g(i)) / (2(u-i))): last x where site i still wins
-        const int i = s[q];
-        const long long num = (long long)u * u - (long long)i * i + (long long)gu - (long long)gs[q];
-        const int w = 1 + (int)(num / (2LL * (u - i)));
-        if (w < n) ++q, s[q] = (short)u, t[q] = (short)w, gs[q] = gu;
+        const wide_t num = (wide_t)u * u - (wide_t)ts * ts + (wide_t)gu - (wide_t)tg;
+        const int w = 1 + (int)(num / (wide_t)(2 * (u - ts)));
+        if (w < n) {
+          st[q] = make_int2(ts | (tt << 16), tg);  // the old top moves to memory
+          ++q, ts = u, tt = w, tg = gu;
+        }
       }
     }
   }
@@ -193,9 +207,12 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
     return;
   }
   for (int u = n - 1; u >= 0; --u) {
-    while (q > 0 && t[q] > u) --q;
-    const int d = u - s[q];
-    const int val = d * d + gs[q];
+    while (q > 0 && tt > u) {
+      const int2 e = st[--q];
+      ts = e.x & 0xffff, tt = (unsigned)e.x >> 16, tg = e.y;
+    }
+    const int d = u - ts;
+    const int val = d * d + tg;
     if (FINAL) {
       double* o = out_d + (int64_t)u * gstride;
       // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360); after resetBuffer old is 10000 everywhere,
