@@ -135,6 +135,47 @@ k_edt_z(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t ncol
   }
 }
 
+// pass z for columns up to 32*NCH voxels: the column's occupancy lives in NCH ballot words held by every
+// lane, both sweeps run on registers and every voxel is written once (the two-sweep kernel above writes,
+// re-reads and re-writes its output: 3x the traffic).
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_edt_z_reg(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t ncols, int nz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t col = wid; col < ncols; col += nw) {
+    const uint8_t* __restrict__ o = occ + col * nz;
+    int32_t* __restrict__ d = out + col * nz;
+    unsigned mask[NCH];
+    int down[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int z = (c << 5) + lane;
+      mask[c] = __ballot_sync(0xffffffffu, z < nz && o[z] != 0);
+    }
+    int last = -kInf;  // nearest occupied voxel at or below, "none yet"
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const unsigned below = mask[c] & (0xffffffffu >> (31 - lane));
+      const int near = below ? ((c << 5) + 31 - __clz(below)) : last;
+      down[c] = (near == -kInf) ? kInf : ((c << 5) + lane - near);
+      if (mask[c]) last = (c << 5) + 31 - __clz(mask[c]);
+    }
+    int next = kInf;  // nearest occupied voxel at or above
+#pragma unroll
+    for (int c = NCH - 1; c >= 0; --c) {
+      const int z = (c << 5) + lane;
+      const unsigned above = mask[c] & (0xffffffffu << lane);
+      const int near = above ? ((c << 5) + __ffs(above) - 1) : next;
+      const int up = (near == kInf) ? kInf : (near - z);
+      const int best = min(down[c], up);
+      if (z < nz) d[z] = (best >= kInf) ? kInf : best * best;
+      if (mask[c]) next = (c << 5) + __ffs(mask[c]) - 1;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // 1-D lower envelope of parabolas on one strided row, exact integer arithmetic.
 //   out[u] = min_i ( (u-i)^2 + g[i] ),   g[i] in [0, kInf]  (kInf = +inf)
@@ -295,7 +336,10 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
     const int threads = 256;
     int64_t blocks = (ncols * 32 + threads - 1) / threads;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    k_edt_z<<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
+    if (nz <= 64) k_edt_z_reg<2><<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
+    else if (nz <= 128) k_edt_z_reg<4><<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
+    else k_edt_z<<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);  // taller columns: the re-read of the
+    // two-sweep kernel hits L1, and it measured faster than 8/16 ballot words in registers (4.05 vs 4.74 ms at nz=400)
   }
   if (ev) cudaEventRecord(ev[1], st);
   const int maxn = nx > ny ? nx : ny;
