@@ -309,8 +309,11 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
 }
 
 bool eval_mma_applicable(const ProbLayout& PL, int64_t traj_offset, int64_t starts_per_problem) {
-  (void)PL, (void)traj_offset;
-  return starts_per_problem % 8 == 0;
+  (void)traj_offset;
+  // Long trajectories: the per-warp staging of the boundary derivatives (8 x 9(m+1) doubles) cuts the resident
+  // warps below what the DMMA formulation needs to hide its latencies; measured on m = 30, N_s = 200 the
+  // general kernel is faster (2.15 vs 2.54 ms per 16,384 batch), so those shapes stay there.
+  return starts_per_problem % 8 == 0 && PL.m <= 12;
 }
 
 cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,

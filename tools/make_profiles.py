@@ -50,9 +50,11 @@ def main():
     # ---- full capture of the dominant kernel ----
     summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, "--hot", "20"],
                           capture_output=True, text=True).stdout
-    with open(os.path.join(out_dir, "%s_k_eval_traj_ncu.txt" % tag), "w") as f:
-        f.write("# %s — ncu --set full --clock-control none --import-source on -k regex:k_eval_traj (one launch of the config-3 "
-                "batch: 65,536 trajectories x 10 segments x 30 samples; 'unit' = one trajectory-segment)\n" % tag)
+    kname = "k_eval_mma" if "mma" in os.path.basename(rep) else "k_eval_traj"
+    with open(os.path.join(out_dir, "%s_%s_ncu.txt" % (tag, kname)), "w") as f:
+        f.write("# %s — ncu --set full --clock-control none --import-source on -k regex:%s (one launch of the config-3 "
+                "batch: 65,536 trajectories x 10 segments x 30 samples; 'unit' = one trajectory-segment = 32 sample slots "
+                "= one warp iteration)\n" % (tag, kname))
         f.write(summ)
     raw = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
                                                       text=True).stdout)))
@@ -63,7 +65,7 @@ def main():
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u[h.index(k)], 1)
 
     traffic = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
-    info = {"k_eval_traj_dram_bytes_per_launch": traffic, "source": "profiles/%s_k_eval_traj_ncu.txt" % tag,
+    info = {"%s_dram_bytes_per_launch" % kname: traffic, "source": "profiles/%s_%s_ncu.txt" % (tag, kname),
             "kernel_time_us_under_ncu": get("gpu__time_duration.sum") if u[h.index("gpu__time_duration.sum")] == "byte" else
             float(d[h.index("gpu__time_duration.sum")].replace(",", ""))}
     json.dump(info, open(os.path.join(out_dir, "roofline_traffic.json"), "w"), indent=1)
