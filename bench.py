@@ -141,6 +141,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the GPU arm has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the one JSON line: some boxes export NCCL_DEBUG=VERSION, which prints on stdout
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 

@@ -78,27 +78,23 @@ __device__ __forceinline__ double f32_round_trip(double x) { return (double)__do
 struct __align__(32) Quad {
   double v00, v01, v10, v11;  // (x0,y0) (x0,y1) (x1,y0) (x1,y1) at one height
 };
-// L1 policy of the corner gathers (GTOP_GATHER_L1: 0 default, 1 no_allocate, 2 evict_first): the
-// gathers stream ~8 KB per warp and iteration through L1; keeping them from displacing the small
-// per-problem tables is what matters (see ldg_tab)
-#ifndef GTOP_GATHER_L1
-#define GTOP_GATHER_L1 1
-#endif
+// L1 policy of the corner gathers.  kNoAlloc: `L1::no_allocate` — with ~30 samples per segment the lines a
+// warp gathers are not touched again by its next iteration (samples 4 apart are ~2.5 voxels apart), and
+// keeping ~8 KB per warp and iteration out of L1 leaves it to the per-problem tables.  With dense sampling
+// (200 samples per segment: 0.1 voxel apart) the next iterations hit the same lines, so those shapes allocate.
+template <bool kNoAlloc>
+__device__ __forceinline__ Quad ldg_quad(const void* p) {
+  Quad q;
+  if (kNoAlloc)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(q.v00), "=d"(q.v01), "=d"(q.v10), "=d"(q.v11) : "l"(p));
+  else
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q.v00), "=d"(q.v01), "=d"(q.v10), "=d"(q.v11) : "l"(p));
+  return q;
+}
 #ifndef GTOP_TABLE_L1
 #define GTOP_TABLE_L1 1
 #endif
-__device__ __forceinline__ Quad ldg_quad(const void* p) {
-  Quad q;
-#if GTOP_GATHER_L1 == 1
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-#elif GTOP_GATHER_L1 == 2
-  asm volatile("ld.global.nc.L1::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
-#else
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-#endif
-               : "=d"(q.v00), "=d"(q.v01), "=d"(q.v10), "=d"(q.v11) : "l"(p));
-  return q;
-}
 // 128-bit load from a per-problem table (sample times, fragments): kept in L1 with evict_last
 __device__ __forceinline__ double2 ldg_tab(const double2* p) {
 #if GTOP_TABLE_L1 == 1
@@ -130,6 +126,7 @@ struct SdfCell {
   bool special;  // !in_map || xlow || ylow: needs the select path of sdf_finish (rare: map border)
 };
 
+template <bool kNoAlloc>
 __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double py, double pz, float fx32, float fy32,
                                            float fz32, SdfCell& c) {
   // isInMap (:55-69) on the float images of the bounds: exact for float-valued positions
@@ -154,8 +151,8 @@ __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double p
 #else
   const char* p = (const char*)S.quad + (size_t)(unsigned)e0 * 32u;
 #endif
-  c.q0 = ldg_quad(p);
-  c.q1 = ldg_quad(p + (z1 - z0) * 128);
+  c.q0 = ldg_quad<kNoAlloc>(p);
+  c.q1 = ldg_quad<kNoAlloc>(p + (z1 - z0) * 128);
 }
 
 // returns dist and the three gradient components (unscaled by 1/res).  The border cases (xlow / ylow /

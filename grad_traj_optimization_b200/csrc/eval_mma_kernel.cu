@@ -100,6 +100,8 @@ __device__ __forceinline__ void coef_phase(const double* __restrict__ Wd, int nr
   }
 }
 
+// kNoAlloc: L1 policy of the gathers (see ldg_quad), chosen from the sampling density.
+template <bool kNoAlloc>
 __global__ void __launch_bounds__(kMmaMaxWarps * 32, GTOP_MMA_MINB)
 k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_problems, EvalScalars E,
            const double* __restrict__ X, int64_t B, int64_t traj_offset, int64_t starts_per_problem,
@@ -194,7 +196,7 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
           pos[a] = (double)pf[a];
         }
         SdfCell cell;
-        sdf_gather(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
+        sdf_gather<kNoAlloc>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const double2 e01 = coef[a * 5 + 3], e23 = coef[a * 5 + 4];
@@ -313,7 +315,8 @@ bool eval_mma_applicable(const ProbLayout& PL, int64_t traj_offset, int64_t star
   // Long trajectories: the per-warp staging of the boundary derivatives (8 x 9(m+1) doubles) cuts the resident
   // warps below what the DMMA formulation needs to hide its latencies; measured on m = 30, N_s = 200 the
   // general kernel is faster (2.15 vs 2.54 ms per 16,384 batch), so those shapes stay there.
-  return starts_per_problem % 8 == 0 && PL.m <= 12;
+  static const int max_m = [] { const char* e = std::getenv("GTOP_MMA_MAX_M"); return e ? std::atoi(e) : 12; }();  // tuning knob
+  return starts_per_problem % 8 == 0 && PL.m <= max_m;
 }
 
 cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
@@ -330,14 +333,15 @@ cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double
     static const long pad = [] { const char* e = std::getenv("GTOP_MMA_SMEM_PAD"); return e ? std::atol(e) : 0L; }();
     smem += (size_t)pad;
   }
+  auto kern = PL.ns_cap <= 64 ? k_eval_mma<true> : k_eval_mma<false>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_eval_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   const int64_t per_cta = (int64_t)wpc * 8;
   const int64_t grid = ((traj_offset & 7) + B + per_cta - 1) / per_cta;
-  k_eval_mma<<<(unsigned)grid, wpc * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset,
-                                                         starts_per_problem, cost, grad, oob_counter);
+  kern<<<(unsigned)grid, wpc * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset, starts_per_problem,
+                                                   cost, grad, oob_counter);
   return cudaGetLastError();
 }
 
