@@ -215,6 +215,35 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
           tc = ldg_tab(reinterpret_cast<const double2*>(tp + 32) + 2);
         }
 
+#ifdef GTOP_EXP_EXTRA_LDS  // sensitivity experiment: +10 coefficient loads (20 L1 wavefronts) per iteration
+        {
+          double sx = 0.0, sy = 0.0;
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            double vx, vy;
+            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(vx), "=d"(vy) : "r"((unsigned)__cvta_generic_to_shared(&coef[q])));
+            sx += vx, sy = vy;
+          }
+          if (sx == 1.2345e300) jseg += sy;
+        }
+#endif
+#ifdef GTOP_EXP_EXTRA_DP  // sensitivity experiment: +20 independent DFMAs per iteration
+        {
+          double e0 = vel[0], e1 = vel[1], e2 = vel[2], e3 = c1[0];
+#pragma unroll
+          for (int q = 0; q < 5; ++q)
+            e0 = fma(e0, 1.0000001, 1e-9), e1 = fma(e1, 1.0000001, 1e-9), e2 = fma(e2, 1.0000001, 1e-9), e3 = fma(e3, 1.0000001, 1e-9);
+          if (e0 + e1 + e2 + e3 == 1.2345e300) jseg += e0;
+        }
+#endif
+#ifdef GTOP_EXP_EXTRA_INT  // sensitivity experiment: a chain of 40 dependent integer instructions per iteration
+        {
+          int k0 = it, k1 = lane;
+#pragma unroll
+          for (int q = 0; q < 20; ++q) k0 = k0 * 3 + k1, k1 = k1 * 5 + k0;
+          if (k0 + k1 == 0x7fffffff) jseg += 1.0;
+        }
+#endif
         const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], fma(vel[0], vel[0], 1e-300)));
         const double vnorm = sqrt_pos(vn2) + 1e-5;  // :358 (the 1e-300 keeps v = 0 finite; absorbed by 1e-5)
         const double inv_vn = rcp_pos(vnorm);
