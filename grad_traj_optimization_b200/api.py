@@ -252,6 +252,32 @@ class ProblemSet:
                                            int(step), cost.data_ptr(), grad.data_ptr(), stream))
 
 
+    def solve_host(self, sdf, X, step=OPT_SECOND_STEP, maxeval=100, traj_offset=0, starts_per_problem=1):
+        """Batched lock-step MMA (the optimiser loop of optimizeTrajectory) on the GPU: returns (best X, min f)."""
+        X = np.array(X, dtype=np.float64, order="C").reshape(-1, self.n)
+        minf = np.empty(X.shape[0])
+        check(lib().gtop_solve_batch_host(sdf.h, self.h, _dp(X), X.shape[0], int(traj_offset), int(starts_per_problem),
+                                          int(step), int(maxeval), _dp(minf)))
+        return X, minf
+
+    def solve_device(self, sdf, X, minf, step=OPT_SECOND_STEP, maxeval=100, traj_offset=0, starts_per_problem=1,
+                     stream=None):
+        """Enqueue the batched solve on device-resident starts (torch CUDA float64 tensors, X updated in place)."""
+        check(lib().gtop_solve_batch_device(sdf.h, self.h, X.data_ptr(), X.shape[0], int(traj_offset),
+                                            int(starts_per_problem), int(step), int(maxeval),
+                                            minf.data_ptr() if minf is not None else None, stream))
+
+
+def mma_minimize(fn_ptr, fn_data, lb, ub, x0, maxeval):
+    """gtop_mma_minimize: host MMA loop around a native nlopt_func (C function pointer + data pointer)."""
+    lb, ub = np.ascontiguousarray(lb, dtype=np.float64), np.ascontiguousarray(ub, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, order="C")
+    minf, nev = C.c_double(0), C.c_int(0)
+    check(lib().gtop_mma_minimize(x.size, fn_ptr, fn_data, _dp(lb), _dp(ub), _dp(x),
+                                  C.cast(C.byref(minf), C.POINTER(C.c_double)), int(maxeval), C.byref(nev)))
+    return x, minf.value, nev.value
+
+
 class Objective:
     """`this` + costFunc: an NLopt-compatible callback bound to one problem of a ProblemSet."""
 

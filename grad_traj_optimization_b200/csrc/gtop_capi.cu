@@ -14,6 +14,7 @@
 
 #include "../../include/gtop_c.h"
 #include "gtop_types.cuh"
+#include "mma_core.cuh"
 #include "problem_setup.hpp"
 
 namespace gtop {
@@ -30,6 +31,25 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
                        bool fresh, cudaStream_t st, cudaEvent_t* ev);
 cudaError_t launch_query(const SdfView& S, const double* pos_dev, int64_t n, double* dist_dev, double* grad_dev,
                          unsigned long long* oob_dev, cudaStream_t st);
+struct SolveView {
+  int n;
+  int64_t B, traj_offset, starts_per_problem;
+  int num_problems;
+  const double* lb;
+  const double* ub;
+  double* xcur;
+  const double* grad;
+  const double* cost;
+  double* x;
+  double* dfdx;
+  double* sigma;
+  double* xprev;
+  double* xprevprev;
+  MmaScalars* sc;
+};
+cudaError_t launch_mma_init(const SolveView& V, cudaStream_t st);
+cudaError_t launch_mma_step(const SolveView& V, int want_candidate, cudaStream_t st);
+cudaError_t launch_mma_finish(const SolveView& V, double* X, double* minf, cudaStream_t st);
 }  // namespace gtop
 
 using namespace gtop;
@@ -81,6 +101,11 @@ struct gtop_problems {
   // staging for the *_host entry point (grown on demand)
   double *dX = nullptr, *dcost = nullptr, *dgrad = nullptr;
   int64_t cap = 0;
+  // workspace of gtop_solve_batch_* (grown on demand): bounds [np][n]; xcur/grad [B][n]; cost [B];
+  // five state vectors [n][B]; scalars [B]
+  double *s_lb = nullptr, *s_ub = nullptr, *s_xcur = nullptr, *s_grad = nullptr, *s_cost = nullptr, *s_state = nullptr;
+  MmaScalars* s_sc = nullptr;
+  int64_t s_cap = 0;
 };
 
 struct gtop_objective_ctx {
@@ -469,6 +494,8 @@ int gtop_problems_destroy(gtop_problems* p) {
   if (!p) return GTOP_OK;
   cudaSetDevice(p->device);
   cudaFree(p->rec), cudaFree(p->oob), cudaFree(p->dX), cudaFree(p->dcost), cudaFree(p->dgrad);
+  cudaFree(p->s_lb), cudaFree(p->s_ub), cudaFree(p->s_xcur), cudaFree(p->s_grad), cudaFree(p->s_cost), cudaFree(p->s_state);
+  cudaFree(p->s_sc);
   for (auto& s : p->streams)
     if (s) cudaStreamDestroy(s);
   for (int i = 0; i < 16; ++i) {
@@ -612,6 +639,108 @@ int gtop_problems_take_out_of_map(gtop_problems* p, int64_t* n) {
   CU(cudaMemcpy(&h, p->oob, sizeof(h), cudaMemcpyDeviceToHost));
   CU(cudaMemset(p->oob, 0, sizeof(h)));
   *n = (int64_t)h;
+  return GTOP_OK;
+}
+
+// ================================================================================ optimiser loop
+int gtop_mma_minimize(unsigned n, gtop_nlopt_func f, void* f_data, const double* lb, const double* ub, double* x,
+                      double* minf, int maxeval, int* evals_done) {
+  REQUIRE(n > 0 && f && lb && ub && x && maxeval >= 1, "bad argument");
+  for (unsigned j = 0; j < n; ++j) REQUIRE(lb[j] <= ub[j] && x[j] >= lb[j] && x[j] <= ub[j], "start outside the bounds");
+  std::vector<double> xcur(x, x + n), g(n), xb(n), gb(n), sigma(n), xp(n), xpp(n);
+  MmaScalars s;
+  const MmaCVec vlb{lb, 1}, vub{ub, 1};
+  mma_init((int)n, vlb, vub, MmaVec{sigma.data(), 1}, s);
+  for (int e = 0; e < maxeval; ++e) {
+    const double fc = f(n, xcur.data(), g.data(), f_data);
+    if (!(fc < HUGE_VAL)) return fail(GTOP_E_STATE, "objective returned HUGE_VAL / NaN (forced stop)");
+    mma_after_eval((int)n, fc, MmaCVec{g.data(), 1}, MmaVec{xb.data(), 1}, MmaVec{gb.data(), 1}, MmaVec{sigma.data(), 1}, vlb,
+                   vub, MmaCVec{xcur.data(), 1}, MmaVec{xp.data(), 1}, MmaVec{xpp.data(), 1}, s);
+    if (e + 1 < maxeval)
+      mma_candidate((int)n, MmaCVec{xb.data(), 1}, MmaCVec{gb.data(), 1}, MmaCVec{sigma.data(), 1}, vlb, vub,
+                    MmaVec{xcur.data(), 1}, s);
+  }
+  std::memcpy(x, xb.data(), sizeof(double) * n);
+  if (minf) *minf = s.fval;
+  if (evals_done) *evals_done = s.evals;
+  return GTOP_OK;
+}
+
+static int solve_workspace(gtop_problems* pr, int64_t B) {
+  const int n = pr->layout.n;
+  if (!pr->host[0].has_path) return fail(GTOP_E_STATE, "the optimiser loop needs the problems' NLopt box (create them from paths)");
+  if (!pr->s_lb) {
+    std::vector<double> lb((size_t)pr->np * n), ub((size_t)pr->np * n);
+    if (int rc = gtop_problems_bounds(pr, lb.data(), ub.data())) return rc;
+    cudaError_t e = cudaMalloc(&pr->s_lb, sizeof(double) * lb.size());
+    if (e == cudaSuccess) e = cudaMalloc(&pr->s_ub, sizeof(double) * ub.size());
+    if (e == cudaSuccess) e = cudaMemcpy(pr->s_lb, lb.data(), sizeof(double) * lb.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(pr->s_ub, ub.data(), sizeof(double) * ub.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("solver bounds: ") + cudaGetErrorString(e));
+  }
+  if (pr->s_cap < B) {
+    cudaFree(pr->s_xcur), cudaFree(pr->s_grad), cudaFree(pr->s_cost), cudaFree(pr->s_state), cudaFree(pr->s_sc);
+    pr->s_xcur = pr->s_grad = pr->s_cost = pr->s_state = nullptr, pr->s_sc = nullptr, pr->s_cap = 0;
+    cudaError_t e = cudaMalloc(&pr->s_xcur, sizeof(double) * B * n);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->s_grad, sizeof(double) * B * n);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->s_cost, sizeof(double) * B);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->s_state, sizeof(double) * 5 * B * n);
+    if (e == cudaSuccess) e = cudaMalloc(&pr->s_sc, sizeof(MmaScalars) * B);
+    if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("solver workspace: ") + cudaGetErrorString(e));
+    pr->s_cap = B;
+  }
+  return GTOP_OK;
+}
+
+int gtop_solve_batch_device(const gtop_sdf* sdf, const gtop_problems* cpr, double* X, int64_t B, int64_t off,
+                            int64_t starts, int step, int maxeval, double* minf, void* stream) {
+  if (int rc = check_eval(sdf, cpr, B, starts, step)) return rc;
+  REQUIRE(maxeval >= 1, "maxeval must be >= 1");
+  if (B == 0) return GTOP_OK;
+  REQUIRE(X, "null device buffer");
+  gtop_problems* pr = const_cast<gtop_problems*>(cpr);  // the workspace is a cache
+  CU(cudaSetDevice(pr->device));
+  if (int rc = solve_workspace(pr, B)) return rc;
+  const int n = pr->layout.n;
+  cudaStream_t st = stream ? (cudaStream_t)stream : pr->streams[0];
+  SolveView V;
+  V.n = n, V.B = B, V.traj_offset = off, V.starts_per_problem = starts, V.num_problems = pr->np;
+  V.lb = pr->s_lb, V.ub = pr->s_ub, V.xcur = pr->s_xcur, V.grad = pr->s_grad, V.cost = pr->s_cost;
+  V.x = pr->s_state, V.dfdx = pr->s_state + (size_t)B * n, V.sigma = pr->s_state + 2 * (size_t)B * n;
+  V.xprev = pr->s_state + 3 * (size_t)B * n, V.xprevprev = pr->s_state + 4 * (size_t)B * n, V.sc = pr->s_sc;
+  CU(cudaMemcpyAsync(V.xcur, X, sizeof(double) * B * n, cudaMemcpyDeviceToDevice, st));
+  CU(launch_mma_init(V, st));
+  const EvalScalars E = make_scalars(pr->prm, step);
+  for (int e = 0; e < maxeval; ++e) {
+    CU(launch_eval(sdf->view, pr->layout, pr->rec, pr->np, E, V.xcur, B, off, starts, pr->s_cost, pr->s_grad, pr->oob, 0, st));
+    CU(launch_mma_step(V, e + 1 < maxeval ? 1 : 0, st));
+    g_launches += 2;
+  }
+  CU(launch_mma_finish(V, X, minf, st));
+  g_launches += 2;
+  return GTOP_OK;
+}
+
+int gtop_solve_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, double* X, int64_t B, int64_t off, int64_t starts,
+                          int step, int maxeval, double* minf) {
+  if (int rc = check_eval(sdf, cpr, B, starts, step)) return rc;
+  if (B == 0) return GTOP_OK;
+  REQUIRE(X, "null host buffer");
+  gtop_problems* pr = const_cast<gtop_problems*>(cpr);
+  CU(cudaSetDevice(pr->device));
+  const int n = pr->layout.n;
+  double *dX = nullptr, *dmin = nullptr;
+  cudaError_t e = cudaMalloc(&dX, sizeof(double) * B * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dmin, sizeof(double) * B);
+  if (e == cudaSuccess) e = cudaMemcpy(dX, X, sizeof(double) * B * n, cudaMemcpyHostToDevice);
+  int rc = GTOP_OK;
+  if (e == cudaSuccess) rc = gtop_solve_batch_device(sdf, cpr, dX, B, off, starts, step, maxeval, dmin, pr->streams[0]);
+  if (e == cudaSuccess && rc == GTOP_OK) e = cudaStreamSynchronize(pr->streams[0]);
+  if (e == cudaSuccess && rc == GTOP_OK) e = cudaMemcpy(X, dX, sizeof(double) * B * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && rc == GTOP_OK && minf) e = cudaMemcpy(minf, dmin, sizeof(double) * B, cudaMemcpyDeviceToHost);
+  cudaFree(dX), cudaFree(dmin);
+  if (rc != GTOP_OK) return rc;
+  CU(e);
   return GTOP_OK;
 }
 

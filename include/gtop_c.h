@@ -170,6 +170,27 @@ int64_t gtop_objective_ctx_evals(const gtop_objective_ctx* ctx);
 /* nlopt_func signature: double f(unsigned n, const double* x, double* grad, void* f_data) */
 double gtop_objective(unsigned n, const double* x, double* grad, void* ctx);
 
+/* ---------------------------------------------------------------- optimiser loop ---- */
+/* Replaces the solver call of GradTrajOptimizer::optimizeTrajectory (grad_traj_optimizer.cpp:135-195:
+ * nlopt::opt(nlopt::algorithm(24) = LD_MMA, n), set_lower/upper_bounds, set_min_objective, optimize) without the
+ * NLopt dependency: Svanberg's MMA for box bounds and no nonlinear constraints, as NLopt 2.5.0 runs it on this
+ * path (csrc/mma_core.cuh), stopping after `maxeval` objective evaluations.
+ *
+ * gtop_mma_minimize: one problem on the host, any objective with NLopt's nlopt_func signature (for example
+ * gtop_objective).  x: in = start (inside the bounds), out = best point; *minf = its value. */
+typedef double (*gtop_nlopt_func)(unsigned n, const double* x, double* grad, void* f_data);
+int gtop_mma_minimize(unsigned n, gtop_nlopt_func f, void* f_data, const double* lb, const double* ub, double* x,
+                      double* minf, int maxeval, int* evals_done);
+/* The same loop for a batch of independent trajectories in lock-step on the GPU: every step is one batched
+ * cost+gradient evaluation (gtop_eval_batch_device) plus one bookkeeping kernel; x never leaves the device.
+ * Bounds are the problems' own NLopt box (gtop_problems_bounds; native / kino path).  X: B x n, in = starts
+ * (clipped into the box), out = best points; minf: B (nullable).  The *_host form copies X in and out. */
+int gtop_solve_batch_device(const gtop_sdf* sdf, const gtop_problems* problems, double* X_dev, int64_t B,
+                            int64_t traj_offset, int64_t starts_per_problem, int step, int maxeval, double* minf_dev,
+                            void* stream);
+int gtop_solve_batch_host(const gtop_sdf* sdf, const gtop_problems* problems, double* X, int64_t B, int64_t traj_offset,
+                          int64_t starts_per_problem, int step, int maxeval, double* minf);
+
 #ifdef __cplusplus
 }
 #endif

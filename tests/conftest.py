@@ -19,3 +19,10 @@ def gtop_lib():
     L = _capi.lib()
     assert L.gtop_device_count() >= 1, "no CUDA device visible: the gpu-marked tests need a B200"
     return L
+
+
+@pytest.fixture(scope="session")
+def gtop_lib_cpu():
+    """The product library for its host-only entry points (no device needed, no compute kernels launched)."""
+    from grad_traj_optimization_b200 import _capi
+    return _capi.lib()
