@@ -67,11 +67,78 @@ struct MmaCVec {
   GTOP_MMA_HD const double& operator[](int j) const { return p[j * stride]; }
 };
 
-GTOP_MMA_HD void mma_init(int n, MmaCVec lb, MmaCVec ub, MmaVec sigma, MmaScalars& s) {
-  for (int j = 0; j < n; ++j) {
-    const double l = lb[j], u = ub[j];
-    sigma[j] = (std::isinf(l) || std::isinf(u)) ? 1.0 : 0.5 * (u - l);
+// ---- per-variable pieces (the batch kernel spreads the variables of a trajectory over the lanes of a warp; the host
+// loop runs them in index order, which reproduces NLopt's arithmetic exactly) ------------------------------------
+
+GTOP_MMA_HD double mma_sigma0(double lb, double ub) { return (std::isinf(lb) || std::isinf(ub)) ? 1.0 : 0.5 * (ub - lb); }
+
+// closed-form minimiser of variable j's term of the separable approximation; adds its share to gsum / wsum
+GTOP_MMA_HD double mma_candidate_var(double xj, double g, double sg, double lo, double hi, double rho, double& gsum,
+                                     double& wsum) {
+  if (sg == 0.0) return xj;  // lb == ub: the variable does not move
+  const double sigma2 = sg * sg;
+  const double v = fabs(g) * sg + 0.5 * rho;
+  const double u = g * sigma2;
+  const double q = u / (v * sg);
+  double dx = (u / v) / (-1.0 - sqrt(fabs(1.0 - q * q)));
+  double xc = xj + dx;
+  if (xc > hi) xc = hi;
+  else if (xc < lo) xc = lo;
+  if (xc > xj + 0.9 * sg) xc = xj + 0.9 * sg;
+  else if (xc < xj - 0.9 * sg) xc = xj - 0.9 * sg;
+  dx = xc - xj;
+  const double dx2 = dx * dx;
+  const double denominv = 1.0 / (sigma2 - dx2);
+  gsum += (g * (sigma2 * dx) + v * dx2) * denominv;
+  wsum += 0.5 * dx2 * denominv;
+  return xc;
+}
+
+// asymptote update of variable j at the end of an outer iteration (from the second one on)
+GTOP_MMA_HD double mma_sigma_update(double sg, double xc, double xp, double xpp, double lo, double hi) {
+  const double dx2 = (xc - xp) * (xp - xpp);
+  sg *= dx2 < 0.0 ? 0.7 : (dx2 > 0.0 ? 1.2 : 1.0);
+  if (!std::isinf(lo) && !std::isinf(hi)) {
+    sg = fmin(sg, 10.0 * (hi - lo));
+    sg = fmax(sg, 0.01 * (hi - lo));
   }
+  return sg;
+}
+
+// What the per-variable bookkeeping has to do after an evaluation; decided from the scalars alone.
+struct MmaDecision {
+  bool accept;       // xcur becomes the approximation point (x, dfdx := xcur, dfdx_cur)
+  bool outer_done;   // the outer iteration ended: xprevprev := xprev, xprev := xcur
+  bool sigma_update; // ... and sigma is updated first (second outer iteration onwards)
+};
+
+// Scalar part of the bookkeeping after f(xcur) = fcur: updates rho / fval / k / evals, returns what to do per variable.
+GTOP_MMA_HD MmaDecision mma_after_eval_scalars(double fcur, MmaScalars& s) {
+  MmaDecision d{false, false, false};
+  ++s.evals;
+  s.fcur = fcur;
+  if (s.evals == 1) {  // f(x0): approximation point = x0; the first outer iteration starts (xprev := x0)
+    s.fval = fcur, s.k = 1;
+    d.accept = true, d.outer_done = true;
+    return d;
+  }
+  const bool inner_done = s.gval >= fcur;
+  if (fcur < s.fval) s.fval = fcur, d.accept = true;  // a better point, inside inner iterations too
+  if (!inner_done) {
+    if (fcur > s.gval) s.rho = fmin(10.0 * s.rho, 1.1 * (s.rho + (fcur - s.gval) / s.wval));
+    return d;
+  }
+  // the outer iteration k ends: new rho and sigma for iteration k+1, then iteration k+1 begins
+  s.rho = fmax(0.1 * s.rho, kMmaRhoMin);
+  d.outer_done = true, d.sigma_update = s.k > 1;
+  ++s.k;
+  return d;
+}
+
+// ---- whole-vector forms (host) -------------------------------------------------------------------------------------
+
+GTOP_MMA_HD void mma_init(int n, MmaCVec lb, MmaCVec ub, MmaVec sigma, MmaScalars& s) {
+  for (int j = 0; j < n; ++j) sigma[j] = mma_sigma0(lb[j], ub[j]);
   s.rho = 1.0, s.k = 0, s.evals = 0, s.fval = s.fcur = s.gval = s.wval = 0.0;
 }
 
@@ -79,32 +146,7 @@ GTOP_MMA_HD void mma_init(int n, MmaCVec lb, MmaCVec ub, MmaVec sigma, MmaScalar
 GTOP_MMA_HD void mma_candidate(int n, MmaCVec x, MmaCVec dfdx, MmaCVec sigma, MmaCVec lb, MmaCVec ub, MmaVec xcur,
                                MmaScalars& s) {
   double gval = s.fval, wval = 0.0;
-  const double rho = s.rho;
-  for (int j = 0; j < n; ++j) {
-    const double xj = x[j], sg = sigma[j];
-    if (sg == 0.0) {  // lb == ub: the variable does not move
-      xcur[j] = xj;
-      continue;
-    }
-    const double g = dfdx[j];
-    const double sigma2 = sg * sg;
-    const double v = fabs(g) * sg + 0.5 * rho;
-    const double u = g * sigma2;
-    const double q = u / (v * sg);
-    double dx = (u / v) / (-1.0 - sqrt(fabs(1.0 - q * q)));
-    double xc = xj + dx;
-    const double hi = ub[j], lo = lb[j];
-    if (xc > hi) xc = hi;
-    else if (xc < lo) xc = lo;
-    if (xc > xj + 0.9 * sg) xc = xj + 0.9 * sg;
-    else if (xc < xj - 0.9 * sg) xc = xj - 0.9 * sg;
-    xcur[j] = xc;
-    dx = xc - xj;
-    const double dx2 = dx * dx;
-    const double denominv = 1.0 / (sigma2 - dx2);
-    gval += (g * (sigma2 * dx) + v * dx2) * denominv;
-    wval += 0.5 * dx2 * denominv;
-  }
+  for (int j = 0; j < n; ++j) xcur[j] = mma_candidate_var(x[j], dfdx[j], sigma[j], lb[j], ub[j], s.rho, gval, wval);
   s.gval = gval, s.wval = wval;
 }
 
@@ -112,41 +154,12 @@ GTOP_MMA_HD void mma_candidate(int n, MmaCVec x, MmaCVec dfdx, MmaCVec sigma, Mm
 // next mma_candidate.  The very first evaluation (at x0 = xcur) only seeds the state.
 GTOP_MMA_HD void mma_after_eval(int n, double fcur, MmaCVec dfdx_cur, MmaVec x, MmaVec dfdx, MmaVec sigma, MmaCVec lb,
                                 MmaCVec ub, MmaCVec xcur, MmaVec xprev, MmaVec xprevprev, MmaScalars& s) {
-  ++s.evals;
-  s.fcur = fcur;
-  if (s.evals == 1) {  // f(x0): approximation point = x0; the first outer iteration starts
-    s.fval = fcur;
-    for (int j = 0; j < n; ++j) x[j] = xcur[j], dfdx[j] = dfdx_cur[j];
-    s.k = 1;
-    for (int j = 0; j < n; ++j) xprev[j] = xcur[j];
-    return;
+  const MmaDecision d = mma_after_eval_scalars(fcur, s);
+  for (int j = 0; j < n; ++j) {
+    if (d.accept) x[j] = xcur[j], dfdx[j] = dfdx_cur[j];
+    if (d.sigma_update) sigma[j] = mma_sigma_update(sigma[j], xcur[j], xprev[j], xprevprev[j], lb[j], ub[j]);
+    if (d.outer_done) xprevprev[j] = xprev[j], xprev[j] = xcur[j];
   }
-  const bool inner_done = s.gval >= fcur;
-  if (fcur < s.fval) {  // a better point: it becomes the approximation point, inside inner iterations too
-    s.fval = fcur;
-    for (int j = 0; j < n; ++j) x[j] = xcur[j], dfdx[j] = dfdx_cur[j];
-  }
-  if (!inner_done) {
-    if (fcur > s.gval) s.rho = fmin(10.0 * s.rho, 1.1 * (s.rho + (fcur - s.gval) / s.wval));
-    return;
-  }
-  // the outer iteration k ends: new rho and sigma for iteration k+1, then iteration k+1 begins
-  s.rho = fmax(0.1 * s.rho, kMmaRhoMin);
-  if (s.k > 1) {
-    for (int j = 0; j < n; ++j) {
-      const double dx2 = (xcur[j] - xprev[j]) * (xprev[j] - xprevprev[j]);
-      const double gam = dx2 < 0.0 ? 0.7 : (dx2 > 0.0 ? 1.2 : 1.0);
-      double sg = sigma[j] * gam;
-      const double l = lb[j], u = ub[j];
-      if (!std::isinf(l) && !std::isinf(u)) {
-        sg = fmin(sg, 10.0 * (u - l));
-        sg = fmax(sg, 0.01 * (u - l));
-      }
-      sigma[j] = sg;
-    }
-  }
-  ++s.k;
-  for (int j = 0; j < n; ++j) xprevprev[j] = xprev[j], xprev[j] = xcur[j];
 }
 
 }  // namespace gtop

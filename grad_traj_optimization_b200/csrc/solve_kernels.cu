@@ -1,9 +1,11 @@
 // solve_kernels.cu — batched lock-step MMA bookkeeping around the cost+gradient kernel (mma_core.cuh).
 //
-// One thread per trajectory runs the per-trajectory state machine between two batched evaluations:
-//   mma_after_eval (accept / rho / sigma / outer-iteration bookkeeping) then mma_candidate (next point).
-// State vectors (x, dfdx, sigma, xprev, xprevprev) are stored [variable][trajectory] so that the threads of a
-// warp touch consecutive addresses; the evaluation kernel's own buffers (xcur, grad) stay [trajectory][variable].
+// One WARP per trajectory runs the per-trajectory state machine between two batched evaluations: the scalar
+// decisions (accept / rho / outer iteration) are taken redundantly by every lane, the per-variable work — copies,
+// asymptote update, the closed-form minimiser of the next approximation — is spread over the lanes (all buffers are
+// [trajectory][variable]: coalesced), and the two sums of the approximation (g, w) are combined with a shuffle
+// butterfly.  (The host loop of gtop_mma_minimize adds them in index order, which is NLopt's order; on the device
+// the objective already differs from the CPU's at the 1e-15 level, so the order of these sums is immaterial.)
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -21,60 +23,92 @@ struct SolveView {
   double* xcur;        // [B][n]  evaluation input
   const double* grad;  // [B][n]  evaluation output
   const double* cost;  // [B]
-  double* x;           // [n][B]  best point
-  double* dfdx;        // [n][B]
-  double* sigma;       // [n][B]
-  double* xprev;       // [n][B]
-  double* xprevprev;   // [n][B]
+  double* x;           // [B][n]  best point
+  double* dfdx;        // [B][n]
+  double* sigma;       // [B][n]
+  double* xprev;       // [B][n]
+  double* xprevprev;   // [B][n]
   MmaScalars* sc;      // [B]
 };
 
+constexpr int kSolveWarps = 4;
+
 // xcur := clip(start, lb, ub); sigma, rho, counters initialised
-__global__ void __launch_bounds__(128) k_mma_init(SolveView V) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kSolveWarps * 32) k_mma_init(SolveView V) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kSolveWarps + (threadIdx.x >> 5);
   if (b >= V.B) return;
   const int64_t pid = ((V.traj_offset + b) / V.starts_per_problem) % V.num_problems;
-  const MmaCVec lb{V.lb + pid * V.n, 1}, ub{V.ub + pid * V.n, 1};
-  double* xc = V.xcur + b * V.n;
-  for (int j = 0; j < V.n; ++j) xc[j] = fmin(fmax(xc[j], lb[j]), ub[j]);
-  MmaScalars s;
-  mma_init(V.n, lb, ub, MmaVec{V.sigma + b, V.B}, s);
-  V.sc[b] = s;
+  const double *lb = V.lb + pid * V.n, *ub = V.ub + pid * V.n;
+  for (int j = lane; j < V.n; j += 32) {
+    const int64_t i = b * V.n + j;
+    V.xcur[i] = fmin(fmax(V.xcur[i], lb[j]), ub[j]);
+    V.sigma[i] = mma_sigma0(lb[j], ub[j]);
+  }
+  if (lane == 0) {
+    MmaScalars s;
+    s.rho = 1.0, s.k = 0, s.evals = 0, s.fval = s.fcur = s.gval = s.wval = 0.0;
+    V.sc[b] = s;
+  }
 }
 
 // after an evaluation of xcur: bookkeeping, then the next candidate into xcur
-__global__ void __launch_bounds__(128) k_mma_step(SolveView V, int want_candidate) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kSolveWarps * 32) k_mma_step(SolveView V, int want_candidate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kSolveWarps + (threadIdx.x >> 5);
   if (b >= V.B) return;
   const int64_t pid = ((V.traj_offset + b) / V.starts_per_problem) % V.num_problems;
-  const MmaCVec lb{V.lb + pid * V.n, 1}, ub{V.ub + pid * V.n, 1};
+  const double *lb = V.lb + pid * V.n, *ub = V.ub + pid * V.n;
   MmaScalars s = V.sc[b];
-  const MmaVec x{V.x + b, V.B}, dfdx{V.dfdx + b, V.B}, sigma{V.sigma + b, V.B}, xprev{V.xprev + b, V.B},
-      xprevprev{V.xprevprev + b, V.B}, xcur{V.xcur + b * V.n, 1};
-  mma_after_eval(V.n, V.cost[b], MmaCVec{V.grad + b * V.n, 1}, x, dfdx, sigma, lb, ub, MmaCVec{xcur.p, 1}, xprev, xprevprev, s);
-  if (want_candidate)
-    mma_candidate(V.n, MmaCVec{x.p, V.B}, MmaCVec{dfdx.p, V.B}, MmaCVec{sigma.p, V.B}, lb, ub, xcur, s);
-  V.sc[b] = s;
+  const MmaDecision d = mma_after_eval_scalars(V.cost[b], s);
+  double gsum = 0.0, wsum = 0.0;
+  for (int j = lane; j < V.n; j += 32) {
+    const int64_t i = b * V.n + j;
+    const double xc = V.xcur[i], lo = lb[j], hi = ub[j];
+    double xj, gj, sg = V.sigma[i];
+    if (d.accept) {
+      xj = xc, gj = V.grad[i];
+      V.x[i] = xj, V.dfdx[i] = gj;
+    } else {
+      xj = V.x[i], gj = V.dfdx[i];
+    }
+    if (d.outer_done) {
+      const double xp = V.xprev[i];
+      if (d.sigma_update) {
+        sg = mma_sigma_update(sg, xc, xp, V.xprevprev[i], lo, hi);
+        V.sigma[i] = sg;
+      }
+      V.xprevprev[i] = xp, V.xprev[i] = xc;
+    }
+    if (want_candidate) V.xcur[i] = mma_candidate_var(xj, gj, sg, lo, hi, s.rho, gsum, wsum);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  }
+  if (want_candidate) s.gval = s.fval + gsum, s.wval = wsum;
+  if (lane == 0) V.sc[b] = s;
 }
 
 // best point back into the caller's [B][n] buffer, best value into minf
-__global__ void __launch_bounds__(128) k_mma_finish(SolveView V, double* __restrict__ X, double* __restrict__ minf) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= V.B) return;
-  for (int j = 0; j < V.n; ++j) X[b * V.n + j] = V.x[(int64_t)j * V.B + b];
-  if (minf) minf[b] = V.sc[b].fval;
+__global__ void __launch_bounds__(256) k_mma_finish(SolveView V, double* __restrict__ X, double* __restrict__ minf) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < V.B * V.n) X[i] = V.x[i];
+  if (minf && i < V.B) minf[i] = V.sc[i].fval;
 }
 
 cudaError_t launch_mma_init(const SolveView& V, cudaStream_t st) {
-  k_mma_init<<<(unsigned)((V.B + 127) / 128), 128, 0, st>>>(V);
+  k_mma_init<<<(unsigned)((V.B + kSolveWarps - 1) / kSolveWarps), kSolveWarps * 32, 0, st>>>(V);
   return cudaGetLastError();
 }
 cudaError_t launch_mma_step(const SolveView& V, int want_candidate, cudaStream_t st) {
-  k_mma_step<<<(unsigned)((V.B + 127) / 128), 128, 0, st>>>(V, want_candidate);
+  k_mma_step<<<(unsigned)((V.B + kSolveWarps - 1) / kSolveWarps), kSolveWarps * 32, 0, st>>>(V, want_candidate);
   return cudaGetLastError();
 }
 cudaError_t launch_mma_finish(const SolveView& V, double* X, double* minf, cudaStream_t st) {
-  k_mma_finish<<<(unsigned)((V.B + 127) / 128), 128, 0, st>>>(V, X, minf);
+  const int64_t tot = V.B * V.n;
+  k_mma_finish<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(V, X, minf);
   return cudaGetLastError();
 }
 
