@@ -1,7 +1,7 @@
 // gtop_harness — ROS-free driver for the B200 GTOP inner loop (stands in for the reference's demo nodes
 // src/opti_node.cpp and src/example_text_input.cpp, which need ROS + RViz).
 //
-//   gtop_harness <config.cfg> [--maxeval N] [--steps 1,2] [--device D] [--nlopt /path/libnlopt.so.0] [--dump out.txt]
+//   gtop_harness <config.cfg> [--maxeval N] [--steps 1,2] [--device D] [--nlopt /path/libnlopt.so.0 | --builtin-mma] [--dump out.txt]
 //
 // Loads a fixture file (configs/*.cfg: map, obstacle recipe, waypoints, parameters), builds the SDF on the GPU
 // (initSDFMap + updateSDFMap), sets the path, prints cost / gradient norm at the initial derivatives, and — when
@@ -122,10 +122,11 @@ double inf_norm(const std::vector<double>& g) {
 
 int main(int argc, char** argv) {
   if (argc < 2) {
-    std::fprintf(stderr, "usage: %s <config.cfg> [--maxeval N] [--steps 1,2] [--device D] [--nlopt PATH] [--dump FILE]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s <config.cfg> [--maxeval N] [--steps 1,2] [--device D] [--nlopt PATH | --builtin-mma] [--dump FILE]\n", argv[0]);
     return 2;
   }
   int maxeval = 100, device = 0;
+  bool builtin = false;
   std::string steps = "2", nlopt_path, dump;
   for (int i = 2; i < argc; ++i) {
     const std::string a = argv[i];
@@ -134,6 +135,7 @@ int main(int argc, char** argv) {
     else if (a == "--steps") steps = next();
     else if (a == "--device") device = std::atoi(next());
     else if (a == "--nlopt") nlopt_path = next();
+    else if (a == "--builtin-mma") builtin = true;
     else if (a == "--dump") dump = next();
   }
   Config cfg;
@@ -165,6 +167,7 @@ int main(int argc, char** argv) {
     }
     if (!nlopt_path.empty()) opt.setNloptLibrary(nlopt_path);
     opt.setMaxEval(maxeval);
+    opt.useBuiltinMma(builtin);
     bool solved = true;
     std::stringstream ss(steps);
     std::string tok;

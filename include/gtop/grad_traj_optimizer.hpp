@@ -102,6 +102,24 @@ class GradTrajOptimizer {
     step_ = step;
     if (!ctx_) check(gtop_objective_ctx_create(sdf_, problems_, 0, step, &ctx_));
     check(gtop_objective_ctx_set_step(ctx_, step));
+    if (builtin_mma_) {  // the library's own LD_MMA loop (csrc/mma_core.cuh): no libnlopt needed
+      if (prm_.algorithm != 24) throw std::runtime_error("the built-in solver only implements algorithm 24 (LD_MMA)");
+      if (max_eval_ <= 0) throw std::runtime_error("the built-in solver stops on setMaxEval(n), n > 0");
+      std::vector<double> xb = dp_;
+      double fb = 0;
+      int nev = 0;
+      vec_cost_.clear(), vec_time_.clear();
+      time_start_ = std::chrono::steady_clock::now();
+      check(gtop_mma_minimize((unsigned)n_, &GradTrajOptimizer::nloptTrampoline, this, lb_.data(), ub_.data(), xb.data(), &fb,
+                              max_eval_, &nev));
+      last_result_ = 5;  // NLOPT_MAXEVAL_REACHED
+      dp_ = xb;
+      coeff_.assign((size_t)m_ * 18, 0.0);
+      check(gtop_coeff_from_x(problems_, 0, dp_.data(), coeff_.data()));
+      last_min_f_ = fb;
+      if (step == 2) iter_num_ = 0, total_time_ = 0;
+      return true;
+    }
     Nlopt& nl = nlopt();
     void* opt = nl.create(prm_.algorithm, (unsigned)n_);  // nlopt::opt(algorithm(alg), 3*num_dp)  :137-138
     if (!opt) throw std::runtime_error("nlopt_create failed");
@@ -161,6 +179,7 @@ class GradTrajOptimizer {
 
   // ---- additions for the ROS-free harness ---------------------------------------------------------
   void setMaxEval(int n) { max_eval_ = n; }                   // deterministic stop
+  void useBuiltinMma(bool on) { builtin_mma_ = on; }          // gtop_mma_minimize instead of libnlopt (LD_MMA only)
   void setNloptLibrary(const std::string& path) { nlopt_path_ = path; }
   double evaluate(const std::vector<double>& x, std::vector<double>& grad, int step) {  // one getCostAndGradient
     need(problems_, "setPath first"), need(sdf_, "initSDFMap / updateSDFMap first");
@@ -262,6 +281,7 @@ class GradTrajOptimizer {
   Nlopt nl_;
   std::string nlopt_path_;
   int m_ = 0, n_ = 0, step_ = 1, max_eval_ = 0, last_result_ = 0, iter_num_ = 0;
+  bool builtin_mma_ = false;
   double last_min_f_ = 0, total_time_ = 0;
   std::vector<double> seg_time_, dp_, lb_, ub_, coeff_, vec_cost_, vec_time_;
   std::chrono::steady_clock::time_point time_start_;

@@ -82,15 +82,17 @@ def test_two_stage_sequence_parity(gtop_lib):
     assert dev <= 1e-4, "trajectory deviation %.3e m" % dev
 
 
+@pytest.mark.parametrize("solver", ["nlopt", "builtin"])
 @pytest.mark.parametrize("name", ["text_input", "opti_node"])
-def test_cpp_harness_end_to_end(gtop_lib, name, tmp_path):
+def test_cpp_harness_end_to_end(gtop_lib, name, solver, tmp_path):
     """The ROS-free C++ harness (GradTrajOptimizer mirror over the C ABI): fixture file -> GPU EDT -> setPath ->
     NLopt solve with the GPU objective; converged coefficients vs the oracle's golden solve."""
     exe = os.path.join(ROOT, "grad_traj_optimization_b200", "gtop_harness")
     assert os.path.exists(exe), "gtop_harness is not built (run __graft_entry__.build())"
     dump = tmp_path / "coeff.txt"
-    r = subprocess.run([exe, os.path.join(ROOT, "configs", name + ".cfg"), "--maxeval", "100", "--steps", "2", "--nlopt",
-                        nlopt_path(), "--dump", str(dump)], capture_output=True, text=True, timeout=300)
+    how = ["--nlopt", nlopt_path()] if solver == "nlopt" else ["--builtin-mma"]  # libnlopt, or the library's own LD_MMA
+    r = subprocess.run([exe, os.path.join(ROOT, "configs", name + ".cfg"), "--maxeval", "100", "--steps", "2"] + how +
+                       ["--dump", str(dump)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     gold_eval = np.load(os.path.join(ROOT, "tests", "golden", "fixtures_eval.npz"))
     gold = np.load(os.path.join(ROOT, "tests", "golden", "fixtures_solve.npz"))
