@@ -113,6 +113,7 @@ struct gtop_objective_ctx {
   const gtop_problems* problems = nullptr;
   int problem = 0, step = 2, n = 0;
   double *hx = nullptr, *hout = nullptr;  // pinned: x[n]; out = cost + grad[n]
+  double *hx_dev = nullptr, *hout_dev = nullptr;  // the same buffers as the device addresses them
   double *dx = nullptr, *dout = nullptr;
   cudaStream_t stream = nullptr;
   int64_t evals = 0;
@@ -752,8 +753,10 @@ int gtop_objective_ctx_create(const gtop_sdf* sdf, const gtop_problems* pr, int3
   CU(cudaSetDevice(pr->device));
   gtop_objective_ctx* c = new gtop_objective_ctx();
   c->sdf = sdf, c->problems = pr, c->problem = problem, c->step = step, c->n = pr->layout.n;
-  cudaError_t e = cudaMallocHost(&c->hx, sizeof(double) * c->n);
-  if (e == cudaSuccess) e = cudaMallocHost(&c->hout, sizeof(double) * (c->n + 1));
+  cudaError_t e = cudaHostAlloc(&c->hx, sizeof(double) * c->n, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostAlloc(&c->hout, sizeof(double) * (c->n + 1), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&c->hx_dev, c->hx, 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&c->hout_dev, c->hout, 0);
   if (e == cudaSuccess) e = cudaMalloc(&c->dx, sizeof(double) * c->n);
   if (e == cudaSuccess) e = cudaMalloc(&c->dout, sizeof(double) * (c->n + 1));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -790,14 +793,13 @@ double gtop_objective(unsigned n, const double* x, double* grad, void* vctx) {
   }
   const gtop_problems* pr = c->problems;
   cudaError_t e = cudaSetDevice(pr->device);
+  // zero-copy: x is read from, and cost/gradient are written to, pinned host memory that the device addresses
+  // directly (unified addressing) — one launch and one synchronisation per call, no copy commands
   std::memcpy(c->hx, x, sizeof(double) * n);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(c->dx, c->hx, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess)
-    e = launch_eval(c->sdf->view, pr->layout, pr->rec, pr->np, make_scalars(pr->prm, c->step), c->dx, 1, c->problem, 1,
-                    c->dout, c->dout + 1, pr->oob, 0, c->stream);
+    e = launch_eval(c->sdf->view, pr->layout, pr->rec, pr->np, make_scalars(pr->prm, c->step), c->hx_dev, 1, c->problem, 1,
+                    c->hout_dev, c->hout_dev + 1, pr->oob, 0, c->stream);
   ++g_launches;
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(c->hout, c->dout, sizeof(double) * (n + 1), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
     g_err = std::string("gtop_objective: ") + cudaGetErrorString(e);

@@ -58,12 +58,14 @@ def main():
         om.set_distance(dist)
         c, g = Cd[0].cpu().numpy(), Gd[0].cpu().numpy()
         ec = eg = 0.0
-        for p in (0, args.sets - 1):
+        full = args.check >= args.starts  # --check >= starts: every trajectory of every waypoint set
+        for p in (range(args.sets) if full else (0, args.sets - 1)):
             opt = oracle_problem(prm, om, wps[p])
             sl = slice(p * args.starts, p * args.starts + min(args.check, args.starts))
             cr, gr, _, _ = opt.eval_batch(X[sl], 2)
             ec, eg = max(ec, rel_cost_err(c[sl], cr).max()), max(eg, rel_grad_err(g[sl], gr).max())
-        print("parity vs oracle: cost %.2e grad %.2e %s" % (ec, eg, "OK" if max(ec, eg) <= 1e-9 else "FAIL"))
+        print("parity vs oracle%s: cost %.2e grad %.2e %s" % (" (all %d trajectories)" % B if full else "", ec, eg,
+                                                             "OK" if max(ec, eg) <= 1e-9 else "FAIL"))
 
 
 if __name__ == "__main__":
