@@ -188,4 +188,102 @@ __device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, doubl
   }
 }
 
+
+// One collision sample of getCostAndGradient (:353-381, optional block :383-407): position / velocity from the
+// segment's coefficients `cb` (c[3][6] then e[3][4] = k*c_k), trilinear SDF, penalties, and the sample's
+// contribution to the 20 per-segment sums v[] (U[a][i] at a*6+i, cost at 18, velocity/acceleration penalty cost
+// at 19).  Shared by the general kernel and the single-trajectory kernel.
+template <bool kVelAcc, bool kWarpUniform>
+__device__ __forceinline__ void sample_accumulate(const SdfView S, const EvalScalars E, const double kA,
+                                                  const double* __restrict__ cb, double t, double t2, double t3, double t4,
+                                                  double t5, const double* __restrict__ xtab, double (&v)[20],
+                                                  unsigned& oob) {
+  double pos[3], vel[3];
+  float pf[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double* c = cb + a * 6;
+    // getPositionFromCoeff (:457-465): left-to-right, unfused, then float
+    double pa = __dadd_rn(c[0], __dmul_rn(c[1], t));
+    pa = __dadd_rn(pa, __dmul_rn(c[2], t2));
+    pa = __dadd_rn(pa, __dmul_rn(c[3], t3));
+    pa = __dadd_rn(pa, __dmul_rn(c[4], t4));
+    pa = __dadd_rn(pa, __dmul_rn(c[5], t5));
+    pf[a] = __double2float_rn(pa);
+    pos[a] = (double)pf[a];
+  }
+  SdfCell cell;
+  sdf_gather<false>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double* c = cb + a * 6;
+    const double* e = cb + 18 + a * 4;
+    // getVelocityFromCoeff (:477-485)
+    double va = __dadd_rn(c[1], __dmul_rn(e[0], t));
+    va = __dadd_rn(va, __dmul_rn(e[1], t2));
+    va = __dadd_rn(va, __dmul_rn(e[2], t3));
+    va = __dadd_rn(va, __dmul_rn(e[3], t4));
+    vel[a] = f32_round_trip(va);
+  }
+  const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], fma(vel[0], vel[0], 1e-300)));
+  const double vnorm = sqrt_pos(vn2) + 1e-5;  // :358 (the 1e-300 keeps v = 0 finite; absorbed by 1e-5)
+  const double inv_vn = rcp_pos(vnorm);
+
+  double dist, g[3];
+  sdf_finish<kWarpUniform>(cell, dist, g[0], g[1], g[2]);
+  oob += cell.in_map ? 0u : 1u;
+
+  // exp(-(d-d0)/r) (:509/:514) = 2^((d0-d)*log2(e)/r)
+  const double ee = exp2_tab(fma(dist, E.neg_log2e_over_r, E.d0_log2e_over_r), xtab);
+  const double ev = ee * vnorm;
+  v[18] += ev;                       // cost: cd*|v| = alpha*ee*vnorm (alpha, dt applied later)
+  // sA_a = gd*grad_a*cd*|v| = kA * ee^2 * vnorm * g_a      (:378, extra cd reproduced — H4)
+  // sB_a = cd*v_a/|v|       = alpha * ee * v_a / vnorm     (:379)
+  const double sAc = kA * (ee * ev);
+  const double sBc = E.alpha * (ee * inv_vn);
+  const double tp2 = 2.0 * t, tp3 = 3.0 * t2, tp4 = 4.0 * t3, tp5 = 5.0 * t4;  // T*V (:379)
+  double sBv[3] = {0.0, 0.0, 0.0}, sCv[3] = {0.0, 0.0, 0.0};
+  if (kVelAcc) {
+    // getAccelerationFromCoeff (:491-505): 2c2 + 6c3 t + 12c4 t^2 + 20c5 t^3, left to right, then float.
+    // 6c3 = 2*(3c3), 12c4 = 3*(4c4), 20c5 = 4*(5c5) round identically from the e_k = k*c_k already held.
+    double cv[3], ca[3], gv[3], gacc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double* e = cb + 18 + a * 4;
+      double aa = __dadd_rn(e[0], __dmul_rn(2.0 * e[1], t));
+      aa = __dadd_rn(aa, __dmul_rn(__dmul_rn(3.0, e[2]), t2));
+      aa = __dadd_rn(aa, __dmul_rn(4.0 * e[3], t3));
+      const double acc = f32_round_trip(aa);
+      const double xv = exp2_tab(fma(fabs(vel[a]), E.log2e_over_rv, E.neg_v0_log2e_over_rv), xtab);
+      const double xa = exp2_tab(fma(fabs(acc), E.log2e_over_ra, E.neg_a0_log2e_over_ra), xtab);
+      cv[a] = E.alpha_v * xv, gv[a] = E.alpha_v_over_r * xv;    // :517-525
+      ca[a] = E.alpha_a * xa, gacc[a] = E.alpha_a_over_r * xa;  // :527-535
+    }
+    v[19] += ((cv[0] + cv[1]) + cv[2] + (ca[0] + ca[1]) + ca[2]) * vnorm;  // cost_vel + cost_acc (:388-392)
+    const double carried = (cv[2] + ca[2]) * inv_vn;  // `cv`, `ca` keep their k = 2 values in the second loop
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      // (gv*|v| + cv*v_a/|v| + ca*v_a/|v|) T V Ldp  and  ga*|v| T V V Ldp   (:396-404), weights wv = wa = 1
+      sBv[a] = E.inv_wc * fma(gv[a], vnorm, carried * vel[a]);
+      sCv[a] = E.inv_wc * (gacc[a] * vnorm);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double sA = sAc * g[a], sB = sBc * vel[a] + sBv[a];
+    v[a * 6 + 0] += sA;
+    v[a * 6 + 1] += fma(sA, t, sB);
+    v[a * 6 + 2] += fma(sA, t2, sB * tp2);
+    v[a * 6 + 3] += fma(sA, t3, sB * tp3);
+    v[a * 6 + 4] += fma(sA, t4, sB * tp4);
+    v[a * 6 + 5] += fma(sA, t5, sB * tp5);
+    if (kVelAcc) {  // T*V*V = (0, 0, 2, 6t, 12t^2, 20t^3)
+      v[a * 6 + 2] = fma(sCv[a], 2.0, v[a * 6 + 2]);
+      v[a * 6 + 3] = fma(sCv[a], 3.0 * tp2, v[a * 6 + 3]);
+      v[a * 6 + 4] = fma(sCv[a], 4.0 * tp3, v[a * 6 + 4]);
+      v[a * 6 + 5] = fma(sCv[a], 5.0 * tp4, v[a * 6 + 5]);
+    }
+  }
+}
+
 }  // namespace gtop

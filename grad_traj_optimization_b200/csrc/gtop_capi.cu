@@ -29,6 +29,11 @@ cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t
                              cudaStream_t st);
 cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
                        bool fresh, cudaStream_t st, cudaEvent_t* ev);
+bool eval_one_applicable(const ProbLayout& PL);
+cudaError_t launch_eval_one(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
+                            const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
+                            int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
+                            cudaStream_t stream);
 cudaError_t launch_query(const SdfView& S, const double* pos_dev, int64_t n, double* dist_dev, double* grad_dev,
                          unsigned long long* oob_dev, cudaStream_t st);
 struct SolveView {
@@ -796,9 +801,16 @@ double gtop_objective(unsigned n, const double* x, double* grad, void* vctx) {
   // zero-copy: x is read from, and cost/gradient are written to, pinned host memory that the device addresses
   // directly (unified addressing) — one launch and one synchronisation per call, no copy commands
   std::memcpy(c->hx, x, sizeof(double) * n);
-  if (e == cudaSuccess)
-    e = launch_eval(c->sdf->view, pr->layout, pr->rec, pr->np, make_scalars(pr->prm, c->step), c->hx_dev, 1, c->problem, 1,
-                    c->hout_dev, c->hout_dev + 1, pr->oob, 0, c->stream);
+  if (e == cudaSuccess) {
+    // one trajectory, latency matters: CTA per trajectory, warp per segment (eval_one_kernel.cu) when m <= 16
+    const EvalScalars E = make_scalars(pr->prm, c->step);
+    if (eval_one_applicable(pr->layout))
+      e = launch_eval_one(c->sdf->view, pr->layout, pr->rec, pr->np, E, c->hx_dev, 1, c->problem, 1, c->hout_dev,
+                          c->hout_dev + 1, pr->oob, c->stream);
+    else
+      e = launch_eval(c->sdf->view, pr->layout, pr->rec, pr->np, E, c->hx_dev, 1, c->problem, 1, c->hout_dev,
+                      c->hout_dev + 1, pr->oob, 0, c->stream);
+  }
   ++g_launches;
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {

@@ -156,7 +156,8 @@ def test_small_collision_weight_skips_sample_pass(gtop_lib):
 
 
 def test_objective_callback_matches_batch(gtop_lib):
-    """gtop_objective (NLopt nlopt_func signature) == one row of the batched evaluation."""
+    """gtop_objective (NLopt nlopt_func signature; its own low-latency kernel: CTA per trajectory, warp per segment)
+    agrees with the rows of the batched evaluation to rounding and meets the parity gate."""
     api = _api()
     cfg = fx.load_cfg("opti_node")
     om = oracle_map_from_cfg(cfg)
@@ -168,10 +169,11 @@ def test_objective_callback_matches_batch(gtop_lib):
     obj = api.Objective(gm, ps, 0, step=2)
     for i in range(3):
         ci, gi = obj(X[i])
-        assert ci == c[i] and np.array_equal(gi, g[i])
+        assert abs(ci - c[i]) <= 1e-12 * abs(c[i]) and rel_grad_err(gi, g[i]).max() <= 1e-12
     assert obj.evals == 3
     c_ref, g_ref, _ = opt.eval(X[1], 2)
-    assert abs(obj(X[1])[0] - c_ref) <= TOL * abs(c_ref)
+    c1, g1 = obj(X[1])
+    assert abs(c1 - c_ref) <= TOL * abs(c_ref) and rel_grad_err(g1, g_ref).max() <= TOL
 
 
 def test_golden_vectors(gtop_lib):
@@ -269,3 +271,8 @@ def test_velocity_acceleration_penalty_flag(gtop_lib, starts):
         c_off, _, _, _ = base.eval_batch(X, step)
         # the block only acts in OPT_SECOND_STEP, and there it must change the objective noticeably
         assert (np.abs(c_ref - c_off).max() > 1e-3 * np.abs(c_off).max()) == (step == 2)
+        # the NLopt callback (single-trajectory kernel) carries the same block
+        obj = api.Objective(gm, ps, 0, step=step)
+        c1, g1 = obj(X[1])
+        assert abs(c1 - c_ref[1]) <= TOL * abs(c_ref[1]) and rel_grad_err(g1, g_ref[1]).max() <= TOL
+        obj.close()
