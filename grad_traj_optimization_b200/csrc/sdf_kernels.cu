@@ -176,6 +176,87 @@ k_edt_z_reg(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t 
   }
 }
 
+// pass z, vectorised: 4 voxels per lane (one 32-bit occupancy load, one 128-bit store), 128 per warp step, for
+// columns with nz % 4 == 0 and nz <= 128*NCH.  The nearest occupied voxel below / above comes from a per-lane scan of
+// its 4 voxels plus a warp max- / min-scan of the lanes' last / first occupied index (shuffles), instead of one ballot
+// round per 32 voxels: ~0.6 warp instructions per voxel instead of 2.2 (the ballot kernel is issue-bound: 79 % issue
+// utilisation at 24 % of DRAM bandwidth on the 2000x2000x400 map).
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_edt_z_vec(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t ncols, int nz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int kNone = 1 << 28;  // "no occupied voxel on that side"
+  for (int64_t col = wid; col < ncols; col += nw) {
+    const uint32_t* __restrict__ o = reinterpret_cast<const uint32_t*>(occ + col * nz);
+    int4* __restrict__ d = reinterpret_cast<int4*>(out + col * nz);
+    uint32_t w[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int z0 = c * 128 + lane * 4;
+      w[c] = z0 < nz ? o[z0 >> 2] : 0u;
+    }
+    // backward sweep: index of the nearest occupied voxel at or above each voxel (kNone if none)
+    int up[NCH][4];
+    int carry = kNone;
+#pragma unroll
+    for (int c = NCH - 1; c >= 0; --c) {
+      const int z0 = c * 128 + lane * 4;
+      // first occupied voxel of this lane
+      int first = kNone;
+#pragma unroll
+      for (int j = 3; j >= 0; --j)
+        if ((w[c] >> (8 * j)) & 0xffu) first = z0 + j;
+      // exclusive min-scan over the HIGHER lanes
+      int sc = first;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_down_sync(0xffffffffu, sc, off);
+        if (lane + off < 32) sc = min(sc, t);
+      }
+      int above = __shfl_down_sync(0xffffffffu, sc, 1);
+      above = (lane == 31) ? carry : min(above, carry);
+      int cur = above;
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {
+        if ((w[c] >> (8 * j)) & 0xffu) cur = z0 + j;
+        up[c][j] = cur;
+      }
+      carry = min(carry, __shfl_sync(0xffffffffu, sc, 0));
+    }
+    // forward sweep: nearest occupied at or below, combine, square, store
+    carry = -kNone;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int z0 = c * 128 + lane * 4;
+      int last = -kNone;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((w[c] >> (8 * j)) & 0xffu) last = z0 + j;
+      int sc = last;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, sc, off);
+        if (lane >= off) sc = max(sc, t);
+      }
+      int below = __shfl_up_sync(0xffffffffu, sc, 1);
+      below = (lane == 0) ? carry : max(below, carry);
+      int cur = below;
+      int r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((w[c] >> (8 * j)) & 0xffu) cur = z0 + j;
+        const int z = z0 + j;
+        const int best = min(z - cur, up[c][j] - z);  // either side may be ~kNone away
+        r[j] = best >= (kNone >> 1) ? kInf : best * best;
+      }
+      if (z0 < nz) d[z0 >> 2] = make_int4(r[0], r[1], r[2], r[3]);
+      carry = max(carry, __shfl_sync(0xffffffffu, sc, 31));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // 1-D lower envelope of parabolas on one strided row, exact integer arithmetic.
 //   out[u] = min_i ( (u-i)^2 + g[i] ),   g[i] in [0, kInf]  (kInf = +inf)
@@ -336,7 +417,10 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
     const int threads = 256;
     int64_t blocks = (ncols * 32 + threads - 1) / threads;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    if (nz <= 64) k_edt_z_reg<2><<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
+    if (nz % 4 == 0 && nz > 128 && nz <= 512) {
+      if (nz <= 256) k_edt_z_vec<2><<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
+      else k_edt_z_vec<4><<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
+    } else if (nz <= 64) k_edt_z_reg<2><<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
     else if (nz <= 128) k_edt_z_reg<4><<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);
     else k_edt_z<<<(unsigned)blocks, threads, 0, st>>>(occ, d1, ncols, nz);  // taller columns: the re-read of the
     // two-sweep kernel hits L1, and it measured faster than 8/16 ballot words in registers (4.05 vs 4.74 ms at nz=400)

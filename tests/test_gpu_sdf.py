@@ -46,7 +46,9 @@ def test_edt_map_a_bit_exact(gtop_lib):
 @pytest.mark.parametrize("dims,nocc,seed", [((7, 5, 3), 3, 1), ((33, 17, 40), 25, 2), ((1, 1, 9), 2, 3), ((40, 1, 1), 3, 4),
                                            ((64, 64, 33), 200, 5), ((20, 70, 65), 1, 6), ((300, 9, 5), 7, 7),
                                            # z-pass variants: ballot words in registers up to nz = 128, two-sweep kernel above
-                                           ((4, 3, 130), 5, 8), ((3, 3, 300), 6, 9), ((2, 3, 530), 4, 10)])
+                                           ((4, 3, 130), 5, 8), ((3, 3, 300), 6, 9), ((2, 3, 530), 4, 10),
+                                           # vectorised z pass (nz % 4 == 0, 128 < nz <= 512): 2 and 4 chunks, edge sizes
+                                           ((5, 2, 256), 9, 11), ((2, 2, 512), 3, 12), ((3, 2, 132), 2, 13), ((2, 2, 260), 1, 14)])
 def test_edt_random_small_grids_vs_bruteforce(gtop_lib, dims, nocc, seed):
     res = 0.25
     size = np.array(dims, dtype=np.float64) * res
