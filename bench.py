@@ -141,10 +141,19 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the GPU arm has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout to the one JSON line: some boxes export NCCL_DEBUG=VERSION, which prints on stdout
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # keep stdout to the ONE JSON line: communicator creation prints "NCCL version ..." on stdout, so stdout
+        # points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     n_gpus = world
 
     full = N_SETS * N_STARTS
