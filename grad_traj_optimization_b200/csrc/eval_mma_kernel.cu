@@ -59,31 +59,35 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // per-warp shared memory, in doubles:
-//   Wd   [8][wstride]   boundary derivatives per trajectory, [3][nrow] in waypoint order (nrow = 3(m+1));
-//                       wstride odd -> the 8 trajectories of a warp sit in distinct banks
+//   ring [8][27]        boundary derivatives of THREE consecutive waypoints per trajectory, [slot][axis][p,v,a]
+//                       with slot = waypoint % 3: segment s needs waypoints s, s+1 for its coefficients and
+//                       s-1, s, s+1 for the smoothness rows of waypoint s, so waypoint s+1 is fetched from x at the
+//                       top of segment s into the slot waypoint s-2 leaves.  Independent of m (a full copy of x
+//                       was 8 x 9(m+1) doubles: 6.3 KB per warp at m = 10, 18 KB at m = 30); stride 27 is odd ->
+//                       the 8 trajectories of a warp sit in distinct banks
 //   coef [8][15][2]     coefficient pairs of the current segment, 15 16-byte elements per trajectory:
 //                       per axis (c0,c1) (c2,c3) (c4,c5) (2c2,3c3) (4c4,5c5).  The 240-byte trajectory
 //                       stride puts the 8 trajectories of a warp in the 8 distinct 16-byte bank groups
 //                       both for the loads (fixed element) and the stores (element varies with the lane)
 //   scr  [8][9]         finished collision-gradient rows of one waypoint (3 axes x p,v,a)
-__host__ __device__ inline int mma_wstride(int m) { return (9 * (m + 1)) | 1; }
-__host__ __device__ inline int mma_warp_smem_doubles(int m) { return 8 * mma_wstride(m) + 240 + 72; }
+constexpr int kRing = 27;
+__host__ __device__ inline int mma_warp_smem_doubles() { return 8 * kRing + 240 + 72; }
 
 // coefficients c[a][i] = sum_r Linv[i][r] * dseg[a][r], summed in ascending dense-column order of L
 // (start derivatives first, except for the last segment whose end derivatives live in columns 3..5
 // of d) with unfused mul/add — the same 6-term sum as `L * d` (:273).  Work item = (axis, power pair).
 template <bool kLast>
-__device__ __forceinline__ void coef_phase(const double* __restrict__ Wd, int nrow, int s,
+__device__ __forceinline__ void coef_phase(const double* __restrict__ wp0, const double* __restrict__ wp1,
                                            const double2* __restrict__ LiTP, double2* __restrict__ coef, int j) {
   for (int item = j; item < 9; item += 4) {
     const int a = item / 3, p = item - 3 * a;
-    const double* w0 = Wd + a * nrow + 3 * s;  // p0,v0,a0,pT,vT,aT contiguous in waypoint order
+    const double *ws = wp0 + 3 * a, *we = wp1 + 3 * a;  // (p,v,a) of the segment's start / end waypoint
     const double2* wt = LiTP + p * 6;
     double q0[6], q1[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       const double2 L = ldg_tab(wt + r);
-      const double w = w0[r];
+      const double w = r < 3 ? ws[r] : we[r - 3];
       q0[r] = __dmul_rn(L.x, w), q1[r] = __dmul_rn(L.y, w);
     }
     double c0, c1;
@@ -107,10 +111,10 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
            const double* __restrict__ X, int64_t B, int64_t traj_offset, int64_t starts_per_problem,
            double* __restrict__ cost_out, double* __restrict__ grad_out, unsigned long long* __restrict__ oob_counter) {
   extern __shared__ __align__(16) double smem[];
-  const int m = PL.m, P = PL.P, n = PL.n, nrow = 3 * (m + 1);
+  const int m = PL.m, P = PL.P, n = PL.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const int g = lane >> 2, j = lane & 3;  // trajectory slot of the warp, sample slot of the iteration
-  const int wstride = mma_wstride(m), per_warp = mma_warp_smem_doubles(m);
+  const int per_warp = mma_warp_smem_doubles();
 
   // 2^(j/16) table for exp2_tab: the only block-level synchronisation of the kernel
   double* xtab = smem + wpc * per_warp;
@@ -127,24 +131,40 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   const int64_t b = b_raw < 0 ? 0 : (b_raw < B ? b_raw : B - 1);  // trajectory of the same group
 
   double* wbase = smem + warp * per_warp;
-  double* Wd = wbase + g * wstride;
-  double2* coef = reinterpret_cast<double2*>(wbase + 8 * wstride) + g * 15;  // this trajectory's 15 pairs
-  double* scr = wbase + 8 * wstride + 240 + g * 9;
+  double* ring = wbase + g * kRing;
+  double2* coef = reinterpret_cast<double2*>(wbase + 8 * kRing) + g * 15;  // this trajectory's 15 pairs
+  double* scr = wbase + 8 * kRing + 240 + g * 9;
 
   // all 8 trajectories of the group belong to one problem (host-checked: starts_per_problem % 8 == 0)
   const int64_t pid = (gb0 / starts_per_problem) % num_problems;
   const double* __restrict__ pr = prob + pid * (int64_t)PL.stride;
   const double* __restrict__ x = X + b * n;
 
-  // ---- 1. boundary derivatives in waypoint order --------------------------------------------------
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-    for (int jj = j; jj < P; jj += 4) Wd[a * nrow + 3 + jj] = x[a * P + jj];
-  for (int o = j; o < 18; o += 4) {
-    const int a = o / 6, r = o - 6 * a;
-    Wd[a * nrow + (r < 3 ? r : 3 * m + (r - 3))] = pr[PL.off_Df + o];
-  }
+  // ---- 1. boundary derivatives of waypoints 0 and 1 into the ring -----------------------------------------
+  // waypoint w: the fixed start / end state (Df) for w = 0 / m, the free derivatives x[a*P + 3(w-1) + q] otherwise
+  auto fetch_waypoint = [&](int w) {
+    double* dst = ring + (w % 3) * 9;
+    for (int i = j; i < 9; i += 4) {
+      const int a = i / 3, q = i - 3 * a;
+      dst[i] = w == 0 ? pr[PL.off_Df + a * 6 + q] : (w == m ? pr[PL.off_Df + a * 6 + 3 + q] : x[a * P + 3 * (w - 1) + q]);
+    }
+  };
+  fetch_waypoint(0);
+  fetch_waypoint(1);
   __syncwarp();
+
+  double Jc = 0.0, js = 0.0;
+  // smoothness cost, rows of the fixed start waypoint (column band of R, :326-327): needs waypoints 0 and 1
+  if (j < 3) {
+    const double* __restrict__ band = pr + PL.off_Rc + j * 9;  // row u = j of waypoint 0; band entries 3..8 <-> wp 0, 1
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double y = 0.0;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) y = fma(ring[(t / 3) * 9 + a * 3 + t % 3], band[3 + t], y);
+      js = fma(y, ring[a * 3 + j], js);
+    }
+  }
 
   // lane constants of the B fragments: column g of the accumulation tiles carries power pw = power_of_col(g);
   // tau_pw = slot[pw], tau'_pw = pw * slot[pw-1] (slot[6] = slot[7] = 0 serve the out-of-range cases)
@@ -153,16 +173,22 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   const double mulB = (pw >= 1 && pw < 6) ? (double)pw : 0.0;
 
   double G[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // back-projected gradient rows (C fragments)
-  double Jc = 0.0, js = 0.0;
   unsigned oob = 0;
   const double kA = -E.alpha * E.alpha_over_r * S.res_inv;  // gd*cd = -(alpha^2/r) e^2; grad scale 1/res
   double* __restrict__ gout = grad_out + b * n;
 
   for (int s = 0; s < m; ++s) {
+    if (s >= 1) {  // waypoint s+1 replaces waypoint s-2 (last read by the combine step of segment s-1)
+      fetch_waypoint(s + 1);
+      __syncwarp();
+    }
+    const double* wpm = ring + ((s + 2) % 3) * 9;  // waypoint s-1 (s >= 1)
+    const double* wp0 = ring + (s % 3) * 9;        // waypoint s
+    const double* wp1 = ring + ((s + 1) % 3) * 9;  // waypoint s+1
     if (!E.skip_collision) {
       const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + s * 36);
-      if (s == m - 1) coef_phase<true>(Wd, nrow, s, LiTP, coef, j);
-      else coef_phase<false>(Wd, nrow, s, LiTP, coef, j);
+      if (s == m - 1) coef_phase<true>(wp0, wp1, LiTP, coef, j);
+      else coef_phase<false>(wp0, wp1, LiTP, coef, j);
       __syncwarp();
 
       const int ns = (int)pr[PL.off_ns + s];
@@ -298,11 +324,14 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
       for (int o = j; o < 9; o += 4) {
         const int a = o / 3, r = o - 3 * a, jj = 3 * (s - 1) + r;
         const double* __restrict__ band = pr + PL.off_Rg + jj * 9;
-        const double* Wb = Wd + a * nrow + 3 * (s - 1);
-        double gs = 0.0;
+        double gs = 0.0;  // window = waypoints s-1, s, s+1 of axis a
 #pragma unroll
-        for (int u = 0; u < 9; ++u) gs = fma(Wb[u], band[u], gs);
-        js = fma(gs, Wb[3 + r], js);
+        for (int u = 0; u < 3; ++u) gs = fma(wpm[a * 3 + u], band[u], gs);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) gs = fma(wp0[a * 3 + u], band[3 + u], gs);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) gs = fma(wp1[a * 3 + u], band[6 + u], gs);
+        js = fma(gs, wp0[a * 3 + r], js);
         const double val = (E.ws * (2.0 * gs) + E.wc * scr[o]) + 1e-5;
         if (live) gout[a * P + jj] = val;
       }
@@ -314,22 +343,21 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
     if (lane == 0 && oob) atomicAdd(oob_counter, (unsigned long long)oob);
   }
 
-  // ---- smoothness cost, fixed rows (first and last waypoint): column band of R (:326-327) -----------
-  for (int o = j; o < 6; o += 4) {
-    const int u = o < 3 ? o : 3 * m + (o - 3);
-    const double* __restrict__ band = pr + PL.off_Rc + u * 9;
-    const int base = o < 3 ? -3 : 3 * m - 3;
-    const int j0 = o < 3 ? 3 : 0, j1 = o < 3 ? 9 : 6;
-    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-    for (int jj = j0; jj < j1; ++jj) {
-      const double bv = band[jj];
-      y0 = fma(Wd[base + jj], bv, y0);
-      y1 = fma(Wd[nrow + base + jj], bv, y1);
-      y2 = fma(Wd[2 * nrow + base + jj], bv, y2);
+  // ---- smoothness cost, rows of the fixed end waypoint (column band of R, :326-327): waypoints m-1 and m, which
+  // the ring still holds after the last segment
+  if (j < 3) {
+    const double* __restrict__ band = pr + PL.off_Rc + (3 * m + j) * 9;  // band entries 0..5 <-> waypoints m-1, m
+    const double* wa = ring + ((m - 1) % 3) * 9;
+    const double* wb = ring + (m % 3) * 9;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double y = 0.0;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) y = fma(wa[a * 3 + t], band[t], y);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) y = fma(wb[a * 3 + t], band[3 + t], y);
+      js = fma(y, wb[a * 3 + j], js);
     }
-    js = fma(y0, Wd[u], js);
-    js = fma(y1, Wd[nrow + u], js);
-    js = fma(y2, Wd[2 * nrow + u], js);
   }
 #pragma unroll
   for (int o = 2; o > 0; o >>= 1) {
@@ -341,10 +369,8 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
 
 bool eval_mma_applicable(const ProbLayout& PL, int64_t traj_offset, int64_t starts_per_problem) {
   (void)traj_offset;
-  // Long trajectories: the per-warp staging of the boundary derivatives (8 x 9(m+1) doubles) cuts the resident
-  // warps below what the DMMA formulation needs to hide its latencies; measured on m = 30, N_s = 200 the
-  // general kernel is faster (2.15 vs 2.54 ms per 16,384 batch), so those shapes stay there.
-  static const int max_m = [] { const char* e = std::getenv("GTOP_MMA_MAX_M"); return e ? std::atoi(e) : 12; }();  // tuning knob
+  // tuning knob: segment-count limit of this kernel (its shared memory no longer depends on m)
+  static const int max_m = [] { const char* e = std::getenv("GTOP_MMA_MAX_M"); return e ? std::atoi(e) : 4096; }();  // tuning knob
   return starts_per_problem % 8 == 0 && PL.m <= max_m;
 }
 
@@ -354,7 +380,7 @@ cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double
                             cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
   // warps per CTA: as many as keep the CTA's shared memory modest (several CTAs per SM)
-  const size_t per_warp = sizeof(double) * (size_t)mma_warp_smem_doubles(PL.m);
+  const size_t per_warp = sizeof(double) * (size_t)mma_warp_smem_doubles();
   int wpc = kMmaMaxWarps;
   while (wpc > 1 && per_warp * wpc + 512 > 40 * 1024) wpc >>= 1;
   size_t smem = per_warp * wpc + kExpTab * sizeof(double);
