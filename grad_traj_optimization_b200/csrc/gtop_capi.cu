@@ -29,6 +29,7 @@ cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t
                              cudaStream_t st);
 cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
                        bool fresh, cudaStream_t st, cudaEvent_t* ev);
+cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev, cudaStream_t st);
 bool eval_one_applicable(const ProbLayout& PL);
 cudaError_t launch_eval_one(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
                             const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
@@ -314,6 +315,22 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
   CU(cudaStreamSynchronize(s->stream));
   for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&s->last_ms[i], s->ev[i], s->ev[i + 1]);
   cudaEventElapsedTime(&s->last_ms[3], s->ev[0], s->ev[3]);
+  return GTOP_OK;
+}
+
+int gtop_debug_check_sqrt(int64_t vmax, int64_t* mismatches) {
+  REQUIRE(mismatches && vmax >= 1 && vmax <= 2147483647LL, "bad argument");
+  REQUIRE(gtop_device_count() >= 1, "no CUDA device (this library has no CPU fallback)");
+  unsigned long long* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(unsigned long long)));
+  cudaError_t e = cudaMemset(d, 0, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = launch_check_sqrt(vmax, d, nullptr);
+  ++g_launches;
+  unsigned long long h = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CU(e);
+  *mismatches = (int64_t)h;
   return GTOP_OK;
 }
 

@@ -258,6 +258,54 @@ k_edt_z_vec(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------
+// ---- cheap exact arithmetic for the envelope passes (they are issue-bound: profiles/r1_microbench.md) ------------
+// floor(num / den) for 0 <= num < 2^31, 0 < den < 2^31: quotient estimate from a Newton-refined FP64 reciprocal
+// (relative error 2^-40, so the estimate is within 1 of the quotient), then an exact remainder fix-up.  ~13
+// instructions against ~30 for the 32-bit integer division sequence.
+__device__ __forceinline__ int floor_div_pos(int num, int den) {
+  const double d = (double)den;
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  y = fma(y, fma(-d, y, 1.0), y);
+  int q = __double2int_rz((double)num * y);
+  const int r = num - q * den;
+  q += (r >= den) ? 1 : 0;
+  q -= (r < 0) ? 1 : 0;
+  return q;
+}
+// sqrt((double)v) correctly rounded for integers 1 <= v <= kFastSqrtMax (= 3 * 8192^2, every value an envelope row
+// of up to 8192 voxels can produce): Goldschmidt step from the MUFU seed plus one exact-residual correction.  The
+// result differs from the true root by < 2^-75 relative before the final rounding; that it IS the correctly rounded
+// value for every v in the range is checked exhaustively on the device (gtop_debug_check_sqrt, tests/test_gpu_sdf.py).
+constexpr int kFastSqrtMax = 3 * 8192 * 8192;
+__device__ __forceinline__ double sqrt_small_int(int v) {
+  const double a = (double)v;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double t = a * y, h = 0.5 * y;
+  const double r = fma(-t, h, 0.5);
+  t = fma(t, r, t), h = fma(h, r, h);
+  return fma(fma(-t, t, a), h, t);
+}
+// res * sqrt(val) as the reference computes it (sdf_map.cpp:356-360), bit for bit
+__device__ __forceinline__ double edt_distance(double res, int val) {
+  if (val == 0) return 0.0 * res;
+  return res * ((val <= kFastSqrtMax) ? sqrt_small_int(val) : sqrt((double)val));
+}
+
+// exhaustive check of sqrt_small_int against the IEEE square root: counts the integers in [1, vmax] where they differ
+__global__ void k_check_sqrt(long long vmax, unsigned long long* mismatches) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (long long v = 1 + (long long)blockIdx.x * blockDim.x + threadIdx.x; v <= vmax; v += stride)
+    bad += (sqrt_small_int((int)v) != sqrt((double)v)) ? 1ull : 0ull;
+  if (bad) atomicAdd(mismatches, bad);
+}
+cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev, cudaStream_t st) {
+  k_check_sqrt<<<148 * 16, 256, 0, st>>>(vmax, mismatches_dev);
+  return cudaGetLastError();
+}
+
 // 1-D lower envelope of parabolas on one strided row, exact integer arithmetic.
 //   out[u] = min_i ( (u-i)^2 + g[i] ),   g[i] in [0, kInf]  (kInf = +inf)
 // Stack of (site, first index where the site wins, g(site)) packed in ONE 8-byte local-memory entry
@@ -309,8 +357,9 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
         q = 0, ts = u, tt = 0, tg = gu;
       } else {
         // Sep(i,u) = floor((u^2 - i^2 + g(u) - g(i)) / (2(u-i))): last x where site i still wins
+        // (num >= 0: the pops above leave a top with F(tt, ts) <= F(tt, u), i.e. num >= 2 tt (u - ts))
         const wide_t num = (wide_t)u * u - (wide_t)ts * ts + (wide_t)gu - (wide_t)tg;
-        const int w = 1 + (int)(num / (wide_t)(2 * (u - ts)));
+        const int w = 1 + ((MAXN <= 8192) ? floor_div_pos((int)num, 2 * (u - ts)) : (int)(num / (wide_t)(2 * (u - ts))));
         if (w < n) {
           st[q] = make_int2(ts | (tt << 16), tg);  // the old top moves to memory
           ++q, ts = u, tt = w, tg = gu;
@@ -339,7 +388,7 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
       double* o = out_d + (int64_t)u * gstride;
       // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360); after resetBuffer old is 10000 everywhere,
       // so the read of the old value is skipped
-      *o = fmin(res * sqrt((double)val), fresh ? 10000.0 : *o);
+      *o = fmin(edt_distance(res, val), fresh ? 10000.0 : *o);
     } else {
       out_i[(int64_t)u * gstride] = val;
     }

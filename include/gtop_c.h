@@ -170,6 +170,10 @@ int64_t gtop_objective_ctx_evals(const gtop_objective_ctx* ctx);
 /* nlopt_func signature: double f(unsigned n, const double* x, double* grad, void* f_data) */
 double gtop_objective(unsigned n, const double* x, double* grad, void* ctx);
 
+/* Self-check of the EDT's fast integer square root: the number of integers v in [1, vmax] for which it differs from
+ * the IEEE sqrt((double)v) that SDFMap::updateESDF3d applies (sdf_map.cpp:356-360).  Must be 0 for vmax = 3*8192^2. */
+int gtop_debug_check_sqrt(int64_t vmax, int64_t* mismatches);
+
 /* ---------------------------------------------------------------- optimiser loop ---- */
 /* Replaces the solver call of GradTrajOptimizer::optimizeTrajectory (grad_traj_optimizer.cpp:135-195:
  * nlopt::opt(nlopt::algorithm(24) = LD_MMA, n), set_lower/upper_bounds, set_min_objective, optimize) without the

@@ -125,3 +125,13 @@ def test_trilinear_query_bit_exact(gtop_lib):
     assert oob_gpu == oob_ref and oob_ref > 100
     assert np.array_equal(d_gpu, d_ref)
     assert np.array_equal(g_gpu, g_ref)
+
+
+def test_fast_integer_sqrt_is_correctly_rounded_everywhere(gtop_lib):
+    """The x pass replaces the library sqrt by a MUFU-seeded Goldschmidt step with an exact-residual correction for
+    squared distances up to 3*8192^2; bit parity of the distance field rests on it being the IEEE value for EVERY
+    integer in that range — checked exhaustively on the device."""
+    import ctypes as C
+    bad = C.c_int64(-1)
+    assert gtop_lib.gtop_debug_check_sqrt(3 * 8192 * 8192, C.byref(bad)) == 0
+    assert bad.value == 0
