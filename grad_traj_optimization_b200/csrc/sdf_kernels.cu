@@ -308,9 +308,10 @@ cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev
 
 // 1-D lower envelope of parabolas on one strided row, exact integer arithmetic.
 //   out[u] = min_i ( (u-i)^2 + g[i] ),   g[i] in [0, kInf]  (kInf = +inf)
-// Stack of (site, first index where the site wins, g(site)) packed in ONE 8-byte local-memory entry
-// per level (rows are < 32768 long: 16-bit site and start), with the top entry held in registers: a
-// push is one 8-byte store, a pop one 8-byte load, the common "compare with the top" touches no memory.
+// Hull entries (first index where the site wins, link to the site below, g(site)) packed in ONE 8-byte
+// local-memory entry per site (rows are < 65535 long: 16-bit start and link), with the top entry held in
+// registers: a push is one coalesced 8-byte store, a pop one 8-byte load, the common "compare with the top"
+// touches no memory.
 // (Three separate arrays cost three uncoalesced local accesses per step: the x pass of the 2000x2000x400
 // map moved 184 GB through L1/L2 for 19 GB of useful traffic.)  F(x,i) = (x-i)^2 + g(i).
 // Rows up to 8192 long keep every intermediate below 2^31 (u^2 + 3 n^2 <= 2.7e8), so the intersection
@@ -320,9 +321,12 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
                                              int32_t* __restrict__ out_i, double* __restrict__ out_d, double res,
                                              bool fresh) {
   typedef typename std::conditional<(MAXN <= 8192), int, long long>::type wide_t;
-  int2 st[MAXN];  // st[q] = (site | start << 16, g(site)) for q below the top
-  int q = -1;     // index of the top entry (kept in ts / tt / tg)
-  int ts = 0, tt = 0, tg = 0;
+  // Hull sites as a linked list embedded in a per-site array: st[u] = (start_u | prev_u << 16, g(u)) is written when
+  // site u is pushed — every lane of a warp is at the same u, so the store is coalesced (a compacted stack indexed by
+  // depth scatters: the depth differs from lane to lane) — and a pop follows the link to a recently written entry.
+  int2 st[MAXN];
+  constexpr int kNoSite = 0xffff;
+  int ts = kNoSite, tt = 0, tg = 0, tp = kNoSite;  // top site, its start, g(top), link to the site below
   // The row loads do not depend on the stack: fetch them kPF elements ahead so that several strided
   // loads are in flight while the envelope logic runs.
   constexpr int kPF = 8;
@@ -342,32 +346,34 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
       const int u = u0 + k, gu = gcur[k];
       if (gu >= kInf) continue;  // an infinite parabola never wins (also pads past the row end)
       // pop while the new parabola is below the top one at the top's start
-      while (q >= 0) {
+      while (ts != kNoSite) {
         const int dq = tt - ts, du = tt - u;
         if ((wide_t)dq * dq + tg > (wide_t)du * du + gu) {
-          if (--q >= 0) {
-            const int2 e = st[q];
-            ts = e.x & 0xffff, tt = (unsigned)e.x >> 16, tg = e.y;
+          ts = tp;
+          if (ts != kNoSite) {
+            const int2 e = st[ts];
+            tt = e.x & 0xffff, tp = (unsigned)e.x >> 16, tg = e.y;
           }
         } else {
           break;
         }
       }
-      if (q < 0) {
-        q = 0, ts = u, tt = 0, tg = gu;
+      if (ts == kNoSite) {
+        ts = u, tt = 0, tg = gu, tp = kNoSite;
+        st[u] = make_int2(tt | (tp << 16), tg);
       } else {
         // Sep(i,u) = floor((u^2 - i^2 + g(u) - g(i)) / (2(u-i))): last x where site i still wins
         // (num >= 0: the pops above leave a top with F(tt, ts) <= F(tt, u), i.e. num >= 2 tt (u - ts))
         const wide_t num = (wide_t)u * u - (wide_t)ts * ts + (wide_t)gu - (wide_t)tg;
         const int w = 1 + ((MAXN <= 8192) ? floor_div_pos((int)num, 2 * (u - ts)) : (int)(num / (wide_t)(2 * (u - ts))));
         if (w < n) {
-          st[q] = make_int2(ts | (tt << 16), tg);  // the old top moves to memory
-          ++q, ts = u, tt = w, tg = gu;
+          tp = ts, ts = u, tt = w, tg = gu;
+          st[u] = make_int2(tt | (tp << 16), tg);
         }
       }
     }
   }
-  if (q < 0) {  // whole row infinite: res*sqrt(DBL_MAX) upstream, never below the old value (<= 10000)
+  if (ts == kNoSite) {  // whole row infinite: res*sqrt(DBL_MAX) upstream, never below the old value (<= 10000)
     for (int u = 0; u < n; ++u) {
       if (FINAL) {
         if (fresh) out_d[(int64_t)u * gstride] = 10000.0;
@@ -378,9 +384,10 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
     return;
   }
   for (int u = n - 1; u >= 0; --u) {
-    while (q > 0 && tt > u) {
-      const int2 e = st[--q];
-      ts = e.x & 0xffff, tt = (unsigned)e.x >> 16, tg = e.y;
+    while (tp != kNoSite && tt > u) {
+      ts = tp;
+      const int2 e = st[ts];
+      tt = e.x & 0xffff, tp = (unsigned)e.x >> 16, tg = e.y;
     }
     const int d = u - ts;
     const int val = d * d + tg;
