@@ -79,7 +79,10 @@ def test_fixture_native_setup_parity(gtop_lib, name):
 @pytest.mark.parametrize("m,n_problems,n_starts,ns", [(6, 16, 64, 30),   # config 2 shape (B = 1,024)
                                                       (10, 4, 256, 30),  # config 3 shape, 4 waypoint sets
                                                       (30, 2, 8, 200),   # config 5 shape
-                                                      (2, 3, 5, 30), (17, 2, 3, 45), (33, 1, 4, 7)])
+                                                      (2, 3, 5, 30), (17, 2, 3, 45), (33, 1, 4, 7),
+                                                      # multi-start (DMMA) kernel: smallest m, sample counts that are not
+                                                      # multiples of 4, more segments than the ring holds waypoints
+                                                      (2, 2, 8, 30), (5, 2, 16, 45), (3, 1, 8, 7), (13, 1, 24, 33)])
 def test_map_a_batches_parity(gtop_lib, m, n_problems, n_starts, ns):
     api = _api()
     om, _ = map_a_oracle()
