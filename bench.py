@@ -245,6 +245,17 @@ def run_ours(args):
         except Exception as exc:  # the headline measurement above does not depend on this leg
             solve = {"error": str(exc)}
 
+    # ---- FP64 ceilings measured in this run ------------------------------------------------
+    fp64 = None
+    if rank == 0:
+        try:
+            import ctypes as C
+            dfma, dmma = C.c_double(0), C.c_double(0)
+            if api.lib().gtop_measure_fp64_peak(local, C.byref(dfma), C.byref(dmma)) == 0:
+                fp64 = {"dfma_peak_tflops": dfma.value, "dmma_peak_tflops": dmma.value}
+        except Exception as exc:
+            fp64 = {"error": str(exc)}
+
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -258,6 +269,13 @@ def run_ours(args):
         peak, peak_kind = measured_peak_gbs()
         achieved = B * bytes_eval / (ms_step * 1e-3) / 1e9  # per-GPU kernel: one launch = B evaluations
         cpu = cpu_baseline(args, X[:min(B, 4096)], starts) if not args.no_cpu_baseline else None
+        if fp64 and "dfma_peak_tflops" in fp64:
+            # executed FP64 work of k_eval_mma per trajectory-segment (ncu, profiles/r1_k_eval_mma_ncu.txt): 122.2
+            # DADD/DMUL/DSETP + 33.5 DFMA warp instructions (32 lanes) + 6.8 DMMA (512 flops each)
+            flops_unit = (62.5 + 56.7 + 3.0) * 32 + 33.5 * 64 + 6.8 * 512
+            tf = flops_unit * M_SEG * B / (ms_step * 1e-3) / 1e12
+            fp64.update({"kernel_executed_tflops": tf, "frac_of_dfma_peak": tf / fp64["dfma_peak_tflops"],
+                         "fp64_unit_busy_ncu": "vector 42.9 % + DMMA 13.6 % of cycles (profiles/r1_k_eval_mma_ncu.txt)"})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -276,6 +294,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * n * 8 + B * 8, "steps": e2e_steps, "host_equals_device": same},
             "gpu_launches": int(launches),
             "solve_on_device": solve,
+            "fp64": fp64,
             "clocks": sampler.summary(),
         }
         print(json.dumps(out))

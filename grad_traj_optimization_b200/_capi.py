@@ -21,7 +21,7 @@ SYMBOLS = (
     "gtop_problems_dense_R", "gtop_problems_Df", "gtop_eval_batch_device", "gtop_eval_batch_host",
     "gtop_problems_take_out_of_map", "gtop_kernel_launch_count", "gtop_coeff_from_x", "gtop_objective_ctx_create",
     "gtop_objective_ctx_set_step", "gtop_objective_ctx_destroy", "gtop_objective_ctx_evals", "gtop_objective",
-    "gtop_mma_minimize", "gtop_solve_batch_device", "gtop_solve_batch_host", "gtop_debug_check_sqrt",
+    "gtop_mma_minimize", "gtop_solve_batch_device", "gtop_solve_batch_host", "gtop_debug_check_sqrt", "gtop_measure_fp64_peak",
 )
 
 
@@ -99,6 +99,7 @@ def lib():
         "gtop_solve_batch_device": (C.c_int, [vp, vp, vp, i64, i64, i64, C.c_int, C.c_int, vp, vp]),
         "gtop_solve_batch_host": (C.c_int, [vp, vp, dp, i64, i64, i64, C.c_int, C.c_int, dp]),
         "gtop_debug_check_sqrt": (C.c_int, [i64, C.POINTER(i64)]),
+        "gtop_measure_fp64_peak": (C.c_int, [C.c_int, dp, dp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():

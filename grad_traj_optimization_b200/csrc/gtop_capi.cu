@@ -29,6 +29,7 @@ cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t
                              cudaStream_t st);
 cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
                        bool fresh, cudaStream_t st, cudaEvent_t* ev);
+cudaError_t measure_fp64_peak(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev, cudaStream_t st);
 bool eval_one_applicable(const ProbLayout& PL);
 cudaError_t launch_eval_one(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
@@ -315,6 +316,15 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
   CU(cudaStreamSynchronize(s->stream));
   for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&s->last_ms[i], s->ev[i], s->ev[i + 1]);
   cudaEventElapsedTime(&s->last_ms[3], s->ev[0], s->ev[3]);
+  return GTOP_OK;
+}
+
+int gtop_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops) {
+  REQUIRE(dfma_tflops && dmma_tflops, "null argument");
+  REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  CU(measure_fp64_peak(dfma_tflops, dmma_tflops, nullptr));
+  g_launches += 4;
   return GTOP_OK;
 }
 

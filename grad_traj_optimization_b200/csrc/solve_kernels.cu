@@ -112,4 +112,64 @@ cudaError_t launch_mma_finish(const SolveView& V, double* X, double* minf, cudaS
   return cudaGetLastError();
 }
 
+// ---- FP64 ceilings of the device (bench.py reports the evaluation kernel against them) ---------------
+// mode 0: independent DFMA chains; mode 1: independent mma.sync.m8n8k4.f64 (DMMA) chains
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double seed) {
+  double x[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = seed + i + threadIdx.x, c[i] = seed * i;
+  const double a = seed * 1.0000001, b = seed * 0.9999999;
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[i]), "+d"(c[i + 1]) : "d"(a), "d"(b));
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i] + c[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+// returns TFLOP/s (DFMA = 2 flops per lane, DMMA m8n8k4 = 512 flops per warp instruction)
+cudaError_t measure_fp64_peak(double* dfma_tflops, double* dmma_tflops, cudaStream_t st) {
+  double* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, 64);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * 8, iters = 8000;
+  const double warps = (double)grid * 8;
+  float ms = 0;
+  for (int mode = 0; mode < 2 && e == cudaSuccess; ++mode) {
+    for (int rep = 0; rep < 2; ++rep) {  // first repetition warms up
+      cudaEventRecord(e0, st);
+      if (mode == 0) k_fp64_peak<0><<<grid, 256, 0, st>>>(out, iters, 1.0);
+      else k_fp64_peak<1><<<grid, 256, 0, st>>>(out, iters, 1.0);
+      cudaEventRecord(e1, st);
+      e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) break;
+      cudaEventElapsedTime(&ms, e0, e1);
+    }
+    const double winst = warps * iters * (mode == 0 ? 32.0 : 4.0);
+    const double tf = winst * (mode == 0 ? 64.0 : 512.0) / (ms * 1e-3) / 1e12;
+    if (mode == 0) *dfma_tflops = tf;
+    else *dmma_tflops = tf;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  cudaFree(out);
+  return e;
+}
+
 }  // namespace gtop

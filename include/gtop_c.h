@@ -170,6 +170,9 @@ int64_t gtop_objective_ctx_evals(const gtop_objective_ctx* ctx);
 /* nlopt_func signature: double f(unsigned n, const double* x, double* grad, void* f_data) */
 double gtop_objective(unsigned n, const double* x, double* grad, void* ctx);
 
+/* Measured FP64 ceilings of the device in TFLOP/s: independent DFMA chains and independent mma.sync.m8n8k4.f64 (DMMA)
+ * chains (about 25 ms).  bench.py reports the evaluation kernel's FP64 work against them. */
+int gtop_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
 /* Self-check of the EDT's fast integer square root: the number of integers v in [1, vmax] for which it differs from
  * the IEEE sqrt((double)v) that SDFMap::updateESDF3d applies (sdf_map.cpp:356-360).  Must be 0 for vmax = 3*8192^2. */
 int gtop_debug_check_sqrt(int64_t vmax, int64_t* mismatches);
