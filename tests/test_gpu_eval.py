@@ -143,7 +143,8 @@ def test_out_of_map_samples_follow_ruling_h3(gtop_lib):
     assert rel_grad_err(g, g_ref).max() <= TOL
 
 
-def test_small_collision_weight_skips_sample_pass(gtop_lib):
+@pytest.mark.parametrize("starts", [4, 8])  # general kernel / multi-start DMMA kernel
+def test_small_collision_weight_skips_sample_pass(gtop_lib, starts):
     """|wc| < 1e-4 breaks out of the segment loop (:346)."""
     api = _api()
     cfg = fx.load_cfg("opti_node")
@@ -152,9 +153,9 @@ def test_small_collision_weight_skips_sample_pass(gtop_lib):
     opt = oracle_problem(prm, om, cfg["waypoints"])
     gm = _gpu_map_from_oracle(om)
     ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(prm))
-    X = _starts(opt, 4, seed=2)
+    X = _starts(opt, starts, seed=2)
     c_ref, g_ref, _, _ = opt.eval_batch(X, 2)
-    c, g, _ = ps.eval_host(gm, X, starts_per_problem=4)
+    c, g, _ = ps.eval_host(gm, X, starts_per_problem=starts)
     assert rel_cost_err(c, c_ref).max() <= TOL and rel_grad_err(g, g_ref).max() <= TOL
 
 
