@@ -46,7 +46,7 @@ namespace gtop {
 
 // resident CTAs per SM asked of the compiler (register cap = 65536 / (32 * warps * MINB))
 #ifndef GTOP_MMA_MINB
-#define GTOP_MMA_MINB 20
+#define GTOP_MMA_MINB 19
 #endif
 // one warp per CTA: the kernel has no block-level cooperation, and small CTAs pack SMs evenly
 #ifndef GTOP_MMA_WARPS
