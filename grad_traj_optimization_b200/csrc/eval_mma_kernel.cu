@@ -33,7 +33,8 @@
 //     the B fragments; the record of the NEXT iteration is requested as soon as the current one is dead
 //     (after the velocity polynomial), so its L2 latency hides behind the second half of the iteration.
 //   * The smoothness cost is accumulated from the gradient rows (d_u * (R d)_u) while they are formed;
-//     only the six fixed rows are left to the tail.
+//     the rows of the fixed start / end state are added before / after the segment loop.
+//   * The boundary derivatives live in a three-waypoint ring per trajectory (shared memory independent of m).
 #include <cuda_runtime.h>
 
 #include <cstdint>
