@@ -8,30 +8,28 @@
 //   warp = 8 trajectories x 4 lanes.  Lane (g, j) = (lane >> 2, lane & 3) evaluates sample 4*it + j of
 //   trajectory g in iteration `it` of the current segment (8 iterations at N_s = 30).
 //
-//   * The per-sample contribution to the 3x6 moment block of the segment,
-//         U[a][i] += sA_a * tau_i + sB_a * tau'_i        (tau = t^i, tau' = i t^(i-1), :376-381)
-//     is a (8 trajectories x 4 samples) x (4 samples x 8 powers) product per axis and per kind, because
-//     tau/tau' only depend on the problem: it is issued as FP64 tensor-core tiles
+//   * The per-sample contribution to the gradient rows of the segment's two waypoints,
+//         G[a][r] += dt * (sA_a * phi_r(t) + sB_a * phi_r'(t)),   phi_r(t) = sum_i t^i Linv[i][r]
+//     (the reference's (gd grad_a cd |v| T + cd v_a/|v| T V) Ldp dt, :376-381, with T Ldp = phi and T V Ldp = phi'),
+//     is a (8 trajectories x 4 samples) x (4 samples x 8 columns) product per axis and per kind, because
+//     phi / phi' only depend on the problem: it is issued as FP64 tensor-core tiles
 //     (mma.sync.m8n8k4.f64, SASS DMMA) — A fragment = the lane's own sA_a (or sB_a), B fragment = a
-//     host-built table, C fragment = 2 accumulators per axis.  The DMMA sums over the 4 lanes of a
-//     trajectory, so there is NO cross-lane shuffle reduction and the accumulators shrink from 19 to 6
-//     doubles per lane.  DMMA shares the FP64 pipe with DFMA on B200 (tools/fp64_peak.cu: 36.9 vs 34.0
-//     TFLOP/s, mixed = sum of both), so this does not buy FP64 throughput; it buys issue slots
-//     (6 DMMA instead of ~50 DFMA/DMUL per sample) and removes the shuffle/shared-memory traffic of
-//     the reduction — the general kernel is L1TEX- and issue-bound, not FP64-bound (profiles/).
-//   * Column c of the accumulation tiles carries power (c>>1) + 4(c&1): lane (g,j) ends up with the
-//     moments of powers (j, 4+j), which are exactly the A fragments of the two k-steps of the
-//     back-projection  G[a][r] = sum_i U[a][i] * dt*Linv[i][r]  (T*Ldp, :378-379) — two more DMMAs per
-//     axis, no data movement in between.
-//   * The back-projection columns alternate with the segment parity (deriv_of_col): the
-//     end-derivative columns of segment s are the start-derivative columns of segment s+1, so the
-//     gradient rows of an interior waypoint accumulate in place in the C fragment across the two
-//     segments that touch it and are written once.
+//     host-built table of dt*phi_r(t_k), dt*phi_r'(t_k), C fragment = 2 accumulators per axis.  The DMMA sums
+//     over the 4 lanes of a trajectory, so there is NO cross-lane shuffle reduction, no separate projection
+//     through Linv, and the accumulators shrink from 19 to 6 doubles per lane.  DMMA shares the FP64 pipe
+//     with DFMA on B200 (tools/fp64_peak.cu: 36.9 vs 34.0 TFLOP/s, mixed = sum of both), so this does not
+//     buy FP64 throughput; it buys issue slots (6 DMMA instead of ~50 DFMA/DMUL per sample) and removes the
+//     shuffle/shared-memory traffic of the reduction — the general kernel is L1TEX- and issue-bound, not
+//     FP64-bound (profiles/).
+//   * The columns alternate with the segment parity (deriv_of_col): the end-derivative columns of
+//     segment s are the start-derivative columns of segment s+1, so the gradient rows of an interior
+//     waypoint accumulate in place in the C fragment across the two segments that touch it and are
+//     written once.
 //   * Coefficients c = L d (:253-279) stay scalar, in the reference's summation order, unfused.
 //   * SDF corners come from the patch-ordered xy-quad copy of the grid: 2 x LDG.256 per sample.
-//   * One 64-byte table record per (problem, segment, sample) feeds both the polynomial evaluation and
-//     the B fragments; the record of the NEXT iteration is requested as soon as the current one is dead
-//     (after the velocity polynomial), so its L2 latency hides behind the second half of the iteration.
+//   * One 64-byte table record per (problem, segment, sample) feeds the polynomial evaluation; the record of
+//     the NEXT iteration is requested as soon as the current one is dead (after the velocity polynomial), so
+//     its L2 latency hides behind the second half of the iteration.
 //   * The smoothness cost is accumulated from the gradient rows (d_u * (R d)_u) while they are formed;
 //     the rows of the fixed start / end state are added before / after the segment loop.
 //   * The boundary derivatives live in a three-waypoint ring per trajectory (shared memory independent of m).
@@ -167,13 +165,7 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
     }
   }
 
-  // lane constants of the B fragments: column g of the accumulation tiles carries power pw = power_of_col(g);
-  // tau_pw = slot[pw], tau'_pw = pw * slot[pw-1] (slot[6] = slot[7] = 0 serve the out-of-range cases)
-  const int pw = power_of_col(g);
-  const int offA = pw, offB = (pw >= 1 && pw < 6) ? pw - 1 : 7;
-  const double mulB = (pw >= 1 && pw < 6) ? (double)pw : 0.0;
-
-  double G[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // back-projected gradient rows (C fragments)
+  double G[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // gradient rows of the two waypoints in flight (C fragments)
   unsigned oob = 0;
   const double kA = -E.alpha * E.alpha_over_r * S.res_inv;  // gd*cd = -(alpha^2/r) e^2; grad scale 1/res
   double* __restrict__ gout = grad_out + b * n;
@@ -203,9 +195,9 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
         tc = ldg_tab(reinterpret_cast<const double2*>(tp) + 2);
       }
 
-      double U[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // moment accumulators (C fragments)
       double jseg = 0.0;
-      for (int it = 0; it < nit; ++it, tp += 32) {
+      const double* __restrict__ php = pr + PL.off_PH + (size_t)(s * PL.nsp + j) * 16;
+      for (int it = 0; it < nit; ++it, tp += 32, php += 64) {
         const double t = ta.y, t2 = tb.x, t3 = tb.y, t4 = tc.x, t5 = tc.y;
         double pos[3], vel[3], c1[3];
         float pf[3];
@@ -234,8 +226,8 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
           va = __dadd_rn(va, __dmul_rn(e23.y, t4));
           vel[a] = f32_round_trip(va);
         }
-        // B fragments of this sample (same 64-byte record: L1 hits), then the record of the next sample
-        const double bA = __ldg(tp + offA), bB = mulB * __ldg(tp + offB);
+        // B fragments of this sample (column g of the lane), then the time record of the next sample
+        const double bA = __ldg(php + g), bB = __ldg(php + 8 + g);
         if (it + 1 < nit) {
           ta = ldg_tab(reinterpret_cast<const double2*>(tp + 32));
           tb = ldg_tab(reinterpret_cast<const double2*>(tp + 32) + 1);
@@ -290,19 +282,12 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
         const double sBc = E.alpha * (ee * inv_vn);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          dmma884(U[a][0], U[a][1], sAc * gd[a], bA);   // += sA_a(sample) * tau_i(sample)
-          dmma884(U[a][0], U[a][1], sBc * vel[a], bB);  // += sB_a(sample) * tau'_i(sample)
+          dmma884(G[a][0], G[a][1], sAc * gd[a], bA);   // += sA_a(sample) * dt phi_r(sample), straight into G
+          dmma884(G[a][0], G[a][1], sBc * vel[a], bB);
         }
       }
       Jc = fma(jseg, pr[PL.off_dt + s], Jc);
 
-      // ---- back-projection through dt*Linv_s: the C fragments of U are the A fragments here -------
-      const double lb0 = pr[PL.off_LB + s * 64 + lane], lb1 = pr[PL.off_LB + s * 64 + 32 + lane];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        dmma884(G[a][0], G[a][1], U[a][0], lb0);  // powers 0..3
-        dmma884(G[a][0], G[a][1], U[a][1], lb1);  // powers 4,5 (6,7 are zero)
-      }
     }
 
     // ---- the rows of waypoint s (start derivatives of segment s) are complete -----------------------

@@ -55,14 +55,16 @@ inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 
 //   LinvT [m][6][6]      transpose of Linv (col = power): the coefficient step reads 6 contiguous
 //                        doubles per derivative instead of a stride-6 column
 // Sections read by the multi-start kernel k_eval_mma (eval_mma_kernel.cu); nsp = ns_cap rounded up to 4:
-//   T8    [m][nsp][8]    per sample slot (1, t, t^2, t^3, t^4, t^5, 0, 0) — one 64-byte record serves the
-//                        polynomial evaluation (t..t^5) AND, read at a lane-dependent offset, the B
-//                        fragments of the accumulation DMMAs (tau_i = t^i, tau'_i = i t^(i-1), :379).
-//                        Padding slots (k >= ns) are all zero: they evaluate the segment's start point and
+//   T8    [m][nsp][8]    per sample slot (1, t, t^2, t^3, t^4, t^5, 0, 0): one 64-byte record for the
+//                        polynomial evaluation.  Padding slots (k >= ns) are all zero: they evaluate the
+//                        segment's start point.
+//   PH    [m][nsp][16]   per sample slot the B fragments of the gradient DMMAs: [c] = dt_s * phi_r(t_k),
+//                        [8 + c] = dt_s * phi_r'(t_k) with phi_r(t) = sum_i t^i Linv_s[i][r] the basis
+//                        function of local derivative r = deriv_of_col(c, s) (T Ldp and T V Ldp of :376-381,
+//                        which depend on the problem only).  Column c <-> derivative r alternates with the
+//                        segment parity so that the end-derivative columns of segment s are the
+//                        start-derivative columns of s+1.  Padding slots and columns 6, 7 are zero: they
 //                        contribute nothing.
-//   LB    [m][2][32]     B fragments of the back-projection DMMAs: dt_s * Linv_s[4*ks + j][r(g)], where
-//                        column g <-> local derivative r alternates with the segment parity so that the
-//                        end-derivative columns of segment s are the start-derivative columns of s+1
 //   LiTP  [m][3][6][2]   (Linv[2p][r], Linv[2p+1][r]): coefficient step, two powers per 128-bit load
 struct ProbLayout {
   int m;       // segments
@@ -71,14 +73,11 @@ struct ProbLayout {
   int ns_cap;  // samples_per_segment (table capacity)
   int nsp;     // ns_cap rounded up to a multiple of 4
   int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df, off_LinvT;
-  int off_T8, off_LB, off_LiTP;
+  int off_T8, off_LiTP, off_PH;
   int stride;
 };
 
-// column c of the accumulation DMMAs carries power kPowerOfCol[c]: lane (g,j) then ends up holding the
-// moments of powers (j, 4+j) — exactly the A fragments of the two back-projection k-steps.
-GTOP_HD inline int power_of_col(int c) { return (c >> 1) + 4 * (c & 1); }
-// local derivative (natural order p0,v0,a0,pT,vT,aT) carried by column c of the back-projection DMMAs
+// local derivative (natural order p0,v0,a0,pT,vT,aT) carried by column c of the gradient DMMAs
 // of segment s; -1 for the two padding columns
 GTOP_HD inline int deriv_of_col(int c, int s) { return c >= 6 ? -1 : ((s & 1) ? (c + 3) % 6 : c); }
 
@@ -101,8 +100,9 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   L.nsp = (ns_cap + 3) & ~3;
   o = (o + 7) & ~7;  // 64-byte aligned slots (relative to the 16-byte aligned record)
   L.off_T8 = o, o += m * L.nsp * 8;
-  L.off_LB = o, o += m * 64;
   L.off_LiTP = o, o += m * 36;
+  o = (o + 7) & ~7;
+  L.off_PH = o, o += m * L.nsp * 16;
   L.stride = (o + 7) & ~7;  // keep every record 64-byte aligned
   return L;
 }

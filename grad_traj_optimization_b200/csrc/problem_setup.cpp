@@ -300,11 +300,21 @@ void pack_record(const ProblemHost& p, double* rec) {
       t8[0] = 1.0;                                               // tau_i = t^i                  (:549)
       for (int q = 1; q <= 5; ++q) t8[q] = tt[(size_t)(q - 1) * NS + k];
     }
-    for (int ks = 0; ks < 2; ++ks)
-      for (int lane = 0; lane < 32; ++lane) {
-        const int g = lane >> 2, i = 4 * ks + (lane & 3), r = deriv_of_col(g, s);
-        rec[L.off_LB + s * 64 + ks * 32 + lane] = (i < 6 && r >= 0) ? p.dt[s] * p.Linv[(size_t)s * 36 + i * 6 + r] : 0.0;
+    // PH[s][k][c] = dt * phi_r(t_k), PH[s][k][8 + c] = dt * phi_r'(t_k), phi_r(t) = sum_i t^i Linv[i][r] the basis
+    // function of local derivative r = deriv_of_col(c, s): T Ldp and T V Ldp of :376-381 times dt (:381)
+    for (int k = 0; k < NSP && k < ns; ++k) {
+      double pw[6] = {1.0, 0, 0, 0, 0, 0};
+      for (int q = 1; q <= 5; ++q) pw[q] = tt[(size_t)(q - 1) * NS + k];
+      double* ph = rec + L.off_PH + ((size_t)s * NSP + k) * 16;
+      for (int c = 0; c < 8; ++c) {
+        const int r = deriv_of_col(c, s);
+        if (r < 0) continue;
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < 6; ++i) a += pw[i] * p.Linv[(size_t)s * 36 + i * 6 + r];
+        for (int i = 1; i < 6; ++i) b += (double)i * pw[i - 1] * p.Linv[(size_t)s * 36 + i * 6 + r];
+        ph[c] = p.dt[s] * a, ph[8 + c] = p.dt[s] * b;
       }
+    }
     for (int pp = 0; pp < 3; ++pp)
       for (int r = 0; r < 6; ++r) {
         rec[L.off_LiTP + s * 36 + (pp * 6 + r) * 2 + 0] = p.Linv[(size_t)s * 36 + (2 * pp) * 6 + r];
