@@ -27,9 +27,10 @@
 //     written once.
 //   * Coefficients c = L d (:253-279) stay scalar, in the reference's summation order, unfused.
 //   * SDF corners come from the patch-ordered xy-quad copy of the grid: 2 x LDG.256 per sample.
-//   * One 64-byte table record per (problem, segment, sample) feeds the polynomial evaluation; the record of
-//     the NEXT iteration is requested as soon as the current one is dead (after the velocity polynomial), so
-//     its L2 latency hides behind the second half of the iteration.
+//   * Per-problem tables are stored in the order the lanes read them (TQ: powers of the sample time, PL: B
+//     fragments), 7 L1 wavefronts per iteration instead of 14 for per-sample records; the time record of the NEXT
+//     iteration is requested as soon as the current one is dead (after the velocity polynomial), so its L2
+//     latency hides behind the second half of the iteration.
 //   * The smoothness cost is accumulated from the gradient rows (d_u * (R d)_u) while they are formed;
 //     the rows of the fixed start / end state are added before / after the segment loop.
 //   * The boundary derivatives live in a three-waypoint ring per trajectory (shared memory independent of m).
@@ -187,17 +188,14 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
       const int ns = (int)pr[PL.off_ns + s];
       const int nit = (ns + 3) >> 2;
       // this lane's 64-byte table record of the current iteration; advanced by 4 slots per iteration
-      const double* __restrict__ tp = pr + PL.off_T8 + (size_t)(s * PL.nsp + j) * 8;
+      const double2* __restrict__ tq = reinterpret_cast<const double2*>(pr + PL.off_TQ) + (size_t)s * (PL.nsp >> 2) * 12 + j;
+      const double2* __restrict__ pl = reinterpret_cast<const double2*>(pr + PL.off_PL) + (size_t)s * (PL.nsp >> 2) * 32 + lane;
+      // lane-ordered tables (gtop_types.cuh): the 4 sample slots of an iteration read 64 contiguous bytes per
+      // load of the time record (1 L1 wavefront), the 32 lanes 512 contiguous bytes of B fragments (4 wavefronts)
       double2 ta, tb, tc;  // (1,t) (t2,t3) (t4,t5) of the current sample, requested one iteration ahead
-      if (nit > 0) {
-        ta = ldg_tab(reinterpret_cast<const double2*>(tp));
-        tb = ldg_tab(reinterpret_cast<const double2*>(tp) + 1);
-        tc = ldg_tab(reinterpret_cast<const double2*>(tp) + 2);
-      }
-
+      if (nit > 0) ta = ldg_tab(tq), tb = ldg_tab(tq + 4), tc = ldg_tab(tq + 8);
       double jseg = 0.0;
-      const double* __restrict__ php = pr + PL.off_PH + (size_t)(s * PL.nsp + j) * 16;
-      for (int it = 0; it < nit; ++it, tp += 32, php += 64) {
+      for (int it = 0; it < nit; ++it, tq += 12, pl += 32) {
         const double t = ta.y, t2 = tb.x, t3 = tb.y, t4 = tc.x, t5 = tc.y;
         double pos[3], vel[3], c1[3];
         float pf[3];
@@ -227,12 +225,9 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
           vel[a] = f32_round_trip(va);
         }
         // B fragments of this sample (column g of the lane), then the time record of the next sample
-        const double bA = __ldg(php + g), bB = __ldg(php + 8 + g);
-        if (it + 1 < nit) {
-          ta = ldg_tab(reinterpret_cast<const double2*>(tp + 32));
-          tb = ldg_tab(reinterpret_cast<const double2*>(tp + 32) + 1);
-          tc = ldg_tab(reinterpret_cast<const double2*>(tp + 32) + 2);
-        }
+        const double2 bAB = ldg_tab(pl);
+        const double bA = bAB.x, bB = bAB.y;
+        if (it + 1 < nit) ta = ldg_tab(tq + 12), tb = ldg_tab(tq + 16), tc = ldg_tab(tq + 20);
 
 #ifdef GTOP_EXP_EXTRA_LDS  // sensitivity experiment: +10 coefficient loads (20 L1 wavefronts) per iteration
         {

@@ -55,13 +55,14 @@ inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 
 //   LinvT [m][6][6]      transpose of Linv (col = power): the coefficient step reads 6 contiguous
 //                        doubles per derivative instead of a stride-6 column
 // Sections read by the multi-start kernel k_eval_mma (eval_mma_kernel.cu); nsp = ns_cap rounded up to 4:
-//   T8    [m][nsp][8]    per sample slot (1, t, t^2, t^3, t^4, t^5, 0, 0): one 64-byte record for the
-//                        polynomial evaluation.  Padding slots (k >= ns) are all zero: they evaluate the
-//                        segment's start point.
-//   PH    [m][nsp][16]   per sample slot the B fragments of the gradient DMMAs: [c] = dt_s * phi_r(t_k),
-//                        [8 + c] = dt_s * phi_r'(t_k) with phi_r(t) = sum_i t^i Linv_s[i][r] the basis
-//                        function of local derivative r = deriv_of_col(c, s) (T Ldp and T V Ldp of :376-381,
-//                        which depend on the problem only).  Column c <-> derivative r alternates with the
+//   TQ    [m][nsp/4][3][4][2]  powers of the sample times in the order the lanes read them: iteration `it` of the
+//                        kernel evaluates samples 4 it + j (j = lane & 3); part 0/1/2 of slot j = (1,t) (t^2,t^3)
+//                        (t^4,t^5), the four slots of a part contiguous (one 64-byte L1 wavefront per 128-bit
+//                        load).  Padding slots (k >= ns) are all zero: they evaluate the segment's start point.
+//   PL    [m][nsp/4][32][2]    B fragments of the gradient DMMAs, one 16-byte pair per lane = 4 g + j of iteration it:
+//                        (dt_s * phi_r(t_k), dt_s * phi_r'(t_k)), k = 4 it + j, phi_r(t) = sum_i t^i Linv_s[i][r] the
+//                        basis function of local derivative r = deriv_of_col(g, s) (T Ldp and T V Ldp of :376-381,
+//                        which depend on the problem only).  Column g <-> derivative r alternates with the
 //                        segment parity so that the end-derivative columns of segment s are the
 //                        start-derivative columns of s+1.  Padding slots and columns 6, 7 are zero: they
 //                        contribute nothing.
@@ -73,7 +74,7 @@ struct ProbLayout {
   int ns_cap;  // samples_per_segment (table capacity)
   int nsp;     // ns_cap rounded up to a multiple of 4
   int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df, off_LinvT;
-  int off_T8, off_LiTP, off_PH;
+  int off_LiTP, off_TQ, off_PL;
   int stride;
 };
 
@@ -99,10 +100,10 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   o = (o + 1) & ~1;
   L.nsp = (ns_cap + 3) & ~3;
   o = (o + 7) & ~7;  // 64-byte aligned slots (relative to the 16-byte aligned record)
-  L.off_T8 = o, o += m * L.nsp * 8;
   L.off_LiTP = o, o += m * 36;
   o = (o + 7) & ~7;
-  L.off_PH = o, o += m * L.nsp * 16;
+  L.off_TQ = o, o += m * (L.nsp / 4) * 24;
+  L.off_PL = o, o += m * (L.nsp / 4) * 64;
   L.stride = (o + 7) & ~7;  // keep every record 64-byte aligned
   return L;
 }

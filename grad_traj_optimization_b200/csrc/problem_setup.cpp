@@ -294,25 +294,22 @@ void pack_record(const ProblemHost& p, double* rec) {
   for (int s = 0; s < p.m; ++s) {
     const double* tt = &p.tt[(size_t)s * 5 * NS];
     const int ns = (int)p.ns[s];
-    for (int k = 0; k < NSP; ++k) {
-      double* t8 = rec + L.off_T8 + ((size_t)s * NSP + k) * 8;  // zero-filled by the memset above
-      if (k >= ns) continue;                                     // padding slot: all zero
-      t8[0] = 1.0;                                               // tau_i = t^i                  (:549)
-      for (int q = 1; q <= 5; ++q) t8[q] = tt[(size_t)(q - 1) * NS + k];
-    }
-    // PH[s][k][c] = dt * phi_r(t_k), PH[s][k][8 + c] = dt * phi_r'(t_k), phi_r(t) = sum_i t^i Linv[i][r] the basis
-    // function of local derivative r = deriv_of_col(c, s): T Ldp and T V Ldp of :376-381 times dt (:381)
+    // TQ / PL (gtop_types.cuh): sample slot k = 4 it + j; padding slots stay zero (memset above)
     for (int k = 0; k < NSP && k < ns; ++k) {
-      double pw[6] = {1.0, 0, 0, 0, 0, 0};
+      const int it = k >> 2, j = k & 3;
+      double pw[6] = {1.0, 0, 0, 0, 0, 0};  // tau_i = t^i (:549)
       for (int q = 1; q <= 5; ++q) pw[q] = tt[(size_t)(q - 1) * NS + k];
-      double* ph = rec + L.off_PH + ((size_t)s * NSP + k) * 16;
-      for (int c = 0; c < 8; ++c) {
-        const int r = deriv_of_col(c, s);
+      double* tq = rec + L.off_TQ + ((size_t)s * (NSP / 4) + it) * 24;
+      for (int part = 0; part < 3; ++part) tq[(part * 4 + j) * 2] = pw[2 * part], tq[(part * 4 + j) * 2 + 1] = pw[2 * part + 1];
+      // (dt * phi_r(t_k), dt * phi_r'(t_k)), phi_r(t) = sum_i t^i Linv[i][r]: T Ldp and T V Ldp of :376-381 times dt (:381)
+      double* pl = rec + L.off_PL + ((size_t)s * (NSP / 4) + it) * 64;
+      for (int g = 0; g < 8; ++g) {
+        const int r = deriv_of_col(g, s);
         if (r < 0) continue;
         double a = 0.0, b = 0.0;
         for (int i = 0; i < 6; ++i) a += pw[i] * p.Linv[(size_t)s * 36 + i * 6 + r];
         for (int i = 1; i < 6; ++i) b += (double)i * pw[i - 1] * p.Linv[(size_t)s * 36 + i * 6 + r];
-        ph[c] = p.dt[s] * a, ph[8 + c] = p.dt[s] * b;
+        pl[(4 * g + j) * 2] = p.dt[s] * a, pl[(4 * g + j) * 2 + 1] = p.dt[s] * b;
       }
     }
     for (int pp = 0; pp < 3; ++pp)
