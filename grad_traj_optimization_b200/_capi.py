@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("GTOP_B200_LIB") or os.path.join(_HERE, "libgtop_b200.
 SYMBOLS = (
     "gtop_abi_version", "gtop_last_error", "gtop_device_count", "gtop_params_default", "gtop_host_alloc",
     "gtop_host_free", "gtop_sdf_create", "gtop_sdf_destroy", "gtop_sdf_grid", "gtop_sdf_reset",
+    "gtop_sdf_reset_range", "gtop_sdf_set_update_range", "gtop_sdf_update_range",
     "gtop_sdf_set_occupancy", "gtop_sdf_set_occupancy_boxes", "gtop_sdf_update_esdf", "gtop_sdf_last_edt_ms",
     "gtop_sdf_download_distance", "gtop_sdf_upload_distance", "gtop_sdf_download_occupancy",
     "gtop_sdf_upload_occupancy", "gtop_sdf_distance_device_ptr", "gtop_sdf_query", "gtop_problems_create_dense",
@@ -63,6 +64,9 @@ def lib():
         "gtop_sdf_destroy": (C.c_int, [vp]),
         "gtop_sdf_grid": (C.c_int, [vp, C.POINTER(i32)]),
         "gtop_sdf_reset": (C.c_int, [vp]),
+        "gtop_sdf_reset_range": (C.c_int, [vp, dp, dp]),
+        "gtop_sdf_set_update_range": (C.c_int, [vp, dp, dp]),
+        "gtop_sdf_update_range": (C.c_int, [vp, C.POINTER(i32)]),
         "gtop_sdf_set_occupancy": (C.c_int, [vp, dp, i64]),
         "gtop_sdf_set_occupancy_boxes": (C.c_int, [vp, C.POINTER(i32), i64]),
         "gtop_sdf_update_esdf": (C.c_int, [vp]),

@@ -71,6 +71,21 @@ class SdfMap:
     def reset(self):
         check(lib().gtop_sdf_reset(self.h))
 
+    def reset_range(self, min_pos, max_pos):
+        """SDFMap::resetBuffer(min_pos, max_pos) (sdf_map.cpp:28-53)."""
+        a, b = _f64(min_pos, (3,)), _f64(max_pos, (3,))
+        check(lib().gtop_sdf_reset_range(self.h, _dp(a), _dp(b)))
+
+    def set_update_range(self, min_pos, max_pos):
+        """SDFMap::setUpdateRange (sdf_map.cpp:244-264): window of the next update_esdf only."""
+        a, b = _f64(min_pos, (3,)), _f64(max_pos, (3,))
+        check(lib().gtop_sdf_set_update_range(self.h, _dp(a), _dp(b)))
+
+    def update_range(self):
+        out = np.zeros(6, dtype=np.int32)
+        check(lib().gtop_sdf_update_range(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out[:3].copy(), out[3:].copy()
+
     def set_occupancy(self, pts):
         p = _f64(pts, (-1, 3))
         check(lib().gtop_sdf_set_occupancy(self.h, _dp(p), p.shape[0]))

@@ -29,6 +29,10 @@ cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t
                              cudaStream_t st);
 cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
                        bool fresh, cudaStream_t st, cudaEvent_t* ev);
+cudaError_t launch_edt_window(const uint8_t* occ, uint8_t* wocc, int32_t* d1, int32_t* d2, double* wdist, double* dist,
+                              const VoxelBox& b, int ny, int nz, double res, cudaStream_t st, cudaEvent_t* ev);
+cudaError_t launch_build_quads_box(const SdfView& S, const double* dist, void* quad, const VoxelBox& b, cudaStream_t st);
+cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, int ny, int nz, double dval, cudaStream_t st);
 cudaError_t measure_fp64_peak(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev, cudaStream_t st);
 bool eval_one_applicable(const ProbLayout& PL);
@@ -93,6 +97,12 @@ struct gtop_sdf {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[4] = {0, 0, 0, 0};
   bool dist_fresh = false;  // distance buffer is 10000 everywhere (just created / reset)
+  // update window of the next gtop_sdf_update_esdf (SDFMap::min_vec / max_vec, sdf_map.cpp:13-14): voxel indices,
+  // inclusive; the whole grid unless gtop_sdf_set_update_range was called since the last update (:366-367)
+  int win_lo[3] = {0, 0, 0}, win_hi[3] = {0, 0, 0};
+  uint8_t* wocc = nullptr;  // compact occupancy / distances of a partial window (grown on demand)
+  double* wdist = nullptr;
+  int64_t wcap = 0;
 };
 
 struct gtop_problems {
@@ -222,6 +232,7 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
     v.hifx = down(v.hix), v.hify = down(v.hiy), v.hifz = down(v.hiz);
   }
   s->nvox = (int64_t)g[0] * g[1] * g[2];
+  for (int i = 0; i < 3; ++i) s->win_lo[i] = 0, s->win_hi[i] = g[i] - 1;
   cudaError_t e = cudaMalloc(&s->dist, sizeof(double) * s->nvox);
   if (e == cudaSuccess) e = cudaMalloc(&s->quad, 32 * (size_t)quad_elems(g[0], g[1], g[2]));
   if (e == cudaSuccess) e = cudaMalloc(&s->occ, s->nvox);
@@ -246,6 +257,7 @@ int gtop_sdf_destroy(gtop_sdf* s) {
   if (!s) return GTOP_OK;
   cudaSetDevice(s->device);
   cudaFree(s->dist), cudaFree(s->quad), cudaFree(s->occ), cudaFree(s->d1), cudaFree(s->d2);
+  cudaFree(s->wocc), cudaFree(s->wdist);
   for (auto& e : s->ev)
     if (e) cudaEventDestroy(e);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -267,6 +279,56 @@ int gtop_sdf_reset(gtop_sdf* s) {
   CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   g_launches += 2;
   CU(cudaStreamSynchronize(s->stream));
+  return GTOP_OK;
+}
+
+// Voxel box of a metric box as resetBuffer / setUpdateRange compute it (sdf_map.cpp:29-43, :248-259): clamp to the map,
+// posToIndex(min_pos), posToIndex(max_pos - res/2) with posToIndex = floor((pos - origin) * res_inv) (:71-74).
+static int metric_box_to_voxels(const gtop_sdf* s, const double min_pos[3], const double max_pos[3], int lo[3], int hi[3]) {
+  const int g[3] = {s->view.nx, s->view.ny, s->view.nz};
+  for (int i = 0; i < 3; ++i) {
+    const double min_range = s->origin[i], max_range = s->origin[i] + s->map_size[i];  // :11-12
+    const double a = std::max(min_pos[i], min_range);
+    const double b = std::min(max_pos[i], max_range) - s->view.res / 2;
+    lo[i] = (int)std::floor((a - s->origin[i]) * s->view.res_inv);
+    hi[i] = (int)std::floor((b - s->origin[i]) * s->view.res_inv);
+    // the reference indexes its buffers with whatever comes out (undefined behaviour for a box outside the map
+    // or an inverted one); here that is an error
+    if (!(a == a) || !(b == b) || lo[i] < 0 || hi[i] > g[i] - 1 || lo[i] > hi[i]) return GTOP_E_INVALID;
+  }
+  return GTOP_OK;
+}
+static VoxelBox window_box(const int lo[3], const int hi[3]) {
+  return VoxelBox{lo[0], lo[1], lo[2], hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, hi[2] - lo[2] + 1};
+}
+
+int gtop_sdf_reset_range(gtop_sdf* s, const double min_pos[3], const double max_pos[3]) {
+  REQUIRE(s && min_pos && max_pos, "null argument");
+  int lo[3], hi[3];
+  if (metric_box_to_voxels(s, min_pos, max_pos, lo, hi) != GTOP_OK)
+    return fail(GTOP_E_INVALID, "reset range: empty box or box outside the map");
+  CU(cudaSetDevice(s->device));
+  const VoxelBox b = window_box(lo, hi);
+  CU(launch_box_reset(s->dist, s->occ, b, s->view.ny, s->view.nz, 10000.0, s->stream));  // sdf_map.cpp:45-52
+  CU(launch_build_quads_box(s->view, s->dist, s->quad, b, s->stream));
+  g_launches += 2;
+  s->dist_fresh = false;  // (conservative: only a whole-grid reset re-arms the read-free x pass)
+  CU(cudaStreamSynchronize(s->stream));
+  return GTOP_OK;
+}
+
+int gtop_sdf_set_update_range(gtop_sdf* s, const double min_pos[3], const double max_pos[3]) {
+  REQUIRE(s && min_pos && max_pos, "null argument");
+  int lo[3], hi[3];
+  if (metric_box_to_voxels(s, min_pos, max_pos, lo, hi) != GTOP_OK)
+    return fail(GTOP_E_INVALID, "update range: empty box or box outside the map");
+  for (int i = 0; i < 3; ++i) s->win_lo[i] = lo[i], s->win_hi[i] = hi[i];
+  return GTOP_OK;
+}
+
+int gtop_sdf_update_range(const gtop_sdf* s, int32_t lo_hi[6]) {
+  REQUIRE(s && lo_hi, "null argument");
+  for (int i = 0; i < 3; ++i) lo_hi[i] = s->win_lo[i], lo_hi[3 + i] = s->win_hi[i];
   return GTOP_OK;
 }
 
@@ -308,11 +370,30 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
     if (e == cudaSuccess) e = cudaMalloc(&s->d2, sizeof(int32_t) * s->nvox);
     if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("edt scratch: ") + cudaGetErrorString(e));
   }
-  CU(launch_edt(s->occ, s->d1, s->d2, s->dist, s->view.nx, s->view.ny, s->view.nz, s->view.res, s->dist_fresh, s->stream,
-                s->ev));
+  const int g[3] = {s->view.nx, s->view.ny, s->view.nz};
+  const bool whole = s->win_lo[0] == 0 && s->win_lo[1] == 0 && s->win_lo[2] == 0 && s->win_hi[0] == g[0] - 1 &&
+                     s->win_hi[1] == g[1] - 1 && s->win_hi[2] == g[2] - 1;
+  if (whole) {
+    CU(launch_edt(s->occ, s->d1, s->d2, s->dist, g[0], g[1], g[2], s->view.res, s->dist_fresh, s->stream, s->ev));
+    CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
+    g_launches += 4;
+  } else {  // the box setUpdateRange left (sdf_map.cpp:244-264)
+    const VoxelBox b = window_box(s->win_lo, s->win_hi);
+    const int64_t n = (int64_t)b.wx * b.wy * b.wz;
+    if (n > s->wcap) {
+      cudaFree(s->wocc), cudaFree(s->wdist);
+      s->wocc = nullptr, s->wdist = nullptr, s->wcap = 0;
+      cudaError_t e = cudaMalloc(&s->wocc, (size_t)n);
+      if (e == cudaSuccess) e = cudaMalloc(&s->wdist, sizeof(double) * (size_t)n);
+      if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("edt window scratch: ") + cudaGetErrorString(e));
+      s->wcap = n;
+    }
+    CU(launch_edt_window(s->occ, s->wocc, s->d1, s->d2, s->wdist, s->dist, b, g[1], g[2], s->view.res, s->stream, s->ev));
+    CU(launch_build_quads_box(s->view, s->dist, s->quad, b, s->stream));
+    g_launches += 6;
+    for (int i = 0; i < 3; ++i) s->win_lo[i] = 0, s->win_hi[i] = g[i] - 1;  // :366-367
+  }
   s->dist_fresh = false;
-  CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
-  g_launches += 4;
   CU(cudaStreamSynchronize(s->stream));
   for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&s->last_ms[i], s->ev[i], s->ev[i + 1]);
   cudaEventElapsedTime(&s->last_ms[3], s->ev[0], s->ev[3]);

@@ -39,6 +39,12 @@ struct SdfView {
   float lofx, lofy, lofz, hifx, hify, hifz;
 };
 
+// a box of voxels [x0, x0+wx) x [y0, y0+wy) x [z0, z0+wz): the update window of SDFMap (min_vec..max_vec,
+// sdf_map.cpp:13-14, :244-264)
+struct VoxelBox {
+  int x0, y0, z0, wx, wy, wz;
+};
+
 // number of 32-byte quad elements of a grid (patch-padded)
 inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 2) * ((ny + 1) / 2) * nz * 4; }
 

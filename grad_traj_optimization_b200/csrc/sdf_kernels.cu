@@ -2,7 +2,8 @@
 // batched trilinear query.
 //
 // Replaces (reference paths relative to EpicOne1/grad_traj_optimization):
-//   SDFMap::resetBuffer       src/sdf_map.cpp:26-53
+//   SDFMap::resetBuffer       src/sdf_map.cpp:26-53   (whole grid: k_fill; a box: k_box_reset)
+//   SDFMap::setUpdateRange    src/sdf_map.cpp:244-264 (updateESDF3d restricted to a box: launch_edt_window)
 //   SDFMap::setOccupancy      src/sdf_map.cpp:80-99   (isInMap :55-69, posToIndex :71-74)
 //   SDFMap::updateESDF3d      src/sdf_map.cpp:310-368 (fillESDF :266-308)
 //   SDFMap::getDistWithGradTrilinear   src/sdf_map.cpp:185-242  (k_query, test / utility path)
@@ -64,6 +65,64 @@ k_build_quads(const double* __restrict__ dist, double2* __restrict__ quad, int n
       q[(sx * 2 + sy) * 2 + 0] = make_double2(v[sx][sy], v[sx][sy + 1]);
       q[(sx * 2 + sy) * 2 + 1] = make_double2(v[sx + 1][sy], v[sx + 1][sy + 1]);
     }
+}
+
+// the same for the quads that read a voxel of a box: patches [pxa, pxa+npx) x [pya, pya+npy), heights [z0, z0+wz)
+__global__ void __launch_bounds__(256)
+k_build_quads_box(const double* __restrict__ dist, double2* __restrict__ quad, int nx, int ny, int nz, int nyh, int pxa,
+                  int pya, int z0, int npy, int wz, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int z = z0 + (int)(i % wz);
+  const int64_t pp = i / wz;
+  const int px = pxa + (int)(pp / npy), py = pya + (int)(pp % npy);
+  const int x = 2 * px, y = 2 * py;
+  double v[3][3];
+#pragma unroll
+  for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int xx = min(x + dx, nx - 1), yy = min(y + dy, ny - 1);
+      v[dx][dy] = dist[((int64_t)xx * ny + yy) * nz + z];
+    }
+  double2* q = quad + (((int64_t)px * nyh + py) * nz + z) * 8;
+#pragma unroll
+  for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+    for (int sy = 0; sy < 2; ++sy) {
+      q[(sx * 2 + sy) * 2 + 0] = make_double2(v[sx][sy], v[sx][sy + 1]);
+      q[(sx * 2 + sy) * 2 + 1] = make_double2(v[sx + 1][sy], v[sx + 1][sy + 1]);
+    }
+}
+
+// voxel i of a box (z fastest) -> index in the full grid
+__device__ __forceinline__ int64_t box_voxel(const VoxelBox& b, int ny, int nz, int64_t i) {
+  const int z = (int)(i % b.wz);
+  const int64_t c = i / b.wz;
+  const int y = (int)(c % b.wy), x = (int)(c / b.wy);
+  return ((int64_t)(b.x0 + x) * ny + (b.y0 + y)) * nz + (b.z0 + z);
+}
+// SDFMap::resetBuffer(min_pos, max_pos) (sdf_map.cpp:28-53): occupancy 0, distance 10000 inside the box
+__global__ void k_box_reset(double* __restrict__ dist, uint8_t* __restrict__ occ, VoxelBox b, int ny, int nz, double dval,
+                            int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t a = box_voxel(b, ny, nz, i);
+  dist[a] = dval;
+  occ[a] = 0;
+}
+__global__ void k_box_gather_occ(const uint8_t* __restrict__ occ, uint8_t* __restrict__ wocc, VoxelBox b, int ny, int nz,
+                                 int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) wocc[i] = occ[box_voxel(b, ny, nz, i)];
+}
+// min(resolution*sqrt(val), old) (sdf_map.cpp:356-360) for the voxels of the box
+__global__ void k_box_merge(const double* __restrict__ wdist, double* __restrict__ dist, VoxelBox b, int ny, int nz,
+                            int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t a = box_voxel(b, ny, nz, i);
+  dist[a] = fmin(wdist[i], dist[a]);
 }
 
 __global__ void k_set_occupancy(SdfView S, uint8_t* __restrict__ occ, const double* __restrict__ pts, int64_t n) {
@@ -450,6 +509,23 @@ cudaError_t launch_build_quads(const SdfView& S, const double* dist, void* quad,
   return cudaGetLastError();
 }
 
+cudaError_t launch_build_quads_box(const SdfView& S, const double* dist, void* quad, const VoxelBox& b, cudaStream_t st) {
+  // quads of voxels (x,y) with x in [x0-1, x0+wx-1], y likewise read a voxel of the box (x+ = x+1, y+ = y+1)
+  const int xa = b.x0 > 0 ? b.x0 - 1 : 0, ya = b.y0 > 0 ? b.y0 - 1 : 0;
+  const int pxa = xa >> 1, pxb = (b.x0 + b.wx - 1) >> 1, pya = ya >> 1, pyb = (b.y0 + b.wy - 1) >> 1;
+  const int npx = pxb - pxa + 1, npy = pyb - pya + 1;
+  const int64_t n = (int64_t)npx * npy * b.wz;
+  k_build_quads_box<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dist, (double2*)quad, S.nx, S.ny, S.nz, S.nyh, pxa, pya,
+                                                                  b.z0, npy, b.wz, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, int ny, int nz, double dval, cudaStream_t st) {
+  const int64_t n = (int64_t)b.wx * b.wy * b.wz;
+  k_box_reset<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dist, occ, b, ny, nz, dval, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_set_occupancy(const SdfView& S, uint8_t* occ, const double* pts_dev, int64_t n, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   k_set_occupancy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S, occ, pts_dev, n);
@@ -498,6 +574,24 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
     return cudaErrorInvalidValue;
   if (ev) cudaEventRecord(ev[3], st);
   return e;
+}
+
+// updateESDF3d restricted to the box [min_vec, max_vec] that setUpdateRange left (sdf_map.cpp:244-264, :310-368):
+// the three envelope passes only run over the rows of the box and only see its occupied voxels, and the result is
+// min'ed into the distance buffer inside the box.  Here: the occupancy of the box is copied into a compact
+// (wx, wy, wz) grid, the SAME exact-integer EDT kernels run on that grid (`fresh`: values capped at 10000), and
+// k_box_merge folds min(new, old) back — identical to the reference's arithmetic because the squared distances are
+// exact integers whatever the coordinate origin of the rows.
+cudaError_t launch_edt_window(const uint8_t* occ, uint8_t* wocc, int32_t* d1, int32_t* d2, double* wdist, double* dist,
+                              const VoxelBox& b, int ny, int nz, double res, cudaStream_t st, cudaEvent_t* ev) {
+  const int64_t n = (int64_t)b.wx * b.wy * b.wz;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  k_box_gather_occ<<<blocks, 256, 0, st>>>(occ, wocc, b, ny, nz, n);
+  cudaError_t e = launch_edt(wocc, d1, d2, wdist, b.wx, b.wy, b.wz, res, true, st, ev);
+  if (e != cudaSuccess) return e;
+  k_box_merge<<<blocks, 256, 0, st>>>(wdist, dist, b, ny, nz, n);
+  if (ev) cudaEventRecord(ev[3], st);  // the merge belongs to the x pass
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -90,6 +90,15 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
 int gtop_sdf_destroy(gtop_sdf* sdf);
 int gtop_sdf_grid(const gtop_sdf* sdf, int32_t grid[3]);
 int gtop_sdf_reset(gtop_sdf* sdf);
+/* SDFMap::resetBuffer(min_pos, max_pos) (src/sdf_map.cpp:28-53): occupancy 0 and distance 10000 inside the metric box
+ * (clamped to the map; voxels posToIndex(min_pos) .. posToIndex(max_pos - res/2)).  GTOP_E_INVALID for an empty box or a box
+ * outside the map (undefined behaviour in the reference). */
+int gtop_sdf_reset_range(gtop_sdf* sdf, const double min_pos[3], const double max_pos[3]);
+/* SDFMap::setUpdateRange (src/sdf_map.cpp:244-264): the NEXT gtop_sdf_update_esdf only runs over this box and only
+ * sees its occupied voxels; afterwards the window is the whole grid again (:366-367). */
+int gtop_sdf_set_update_range(gtop_sdf* sdf, const double min_pos[3], const double max_pos[3]);
+/* current update window (SDFMap::min_vec, max_vec): lo_hi = {x0,y0,z0, x1,y1,z1}, inclusive voxel indices */
+int gtop_sdf_update_range(const gtop_sdf* sdf, int32_t lo_hi[6]);
 int gtop_sdf_set_occupancy(gtop_sdf* sdf, const double* xyz /* n x 3, host */, int64_t n);
 /* extension for large synthetic maps: mark whole voxel boxes [lo, hi] (inclusive, clipped), n x 6 int32 host */
 int gtop_sdf_set_occupancy_boxes(gtop_sdf* sdf, const int32_t* lo_hi, int64_t n);

@@ -72,6 +72,9 @@ def lib():
         "gto_map_destroy": (None, [vp]),
         "gto_map_grid": (None, [vp, C.POINTER(C.c_int)]),
         "gto_map_reset": (None, [vp]),
+        "gto_map_reset_range": (None, [vp, dp, dp]),
+        "gto_map_set_update_range": (None, [vp, dp, dp]),
+        "gto_map_update_range": (None, [vp, C.POINTER(C.c_int32)]),
         "gto_map_set_occupancy": (None, [vp, dp, i64]),
         "gto_map_update_esdf": (None, [vp]),
         "gto_map_get_distance": (None, [vp, dp]),
@@ -136,6 +139,21 @@ class OracleMap:
 
     def reset(self):
         lib().gto_map_reset(self.h)
+
+    def reset_range(self, min_pos, max_pos):
+        """SDFMap::resetBuffer(min_pos, max_pos) (sdf_map.cpp:28-53)."""
+        a, b = np.asarray(min_pos, dtype=np.float64), np.asarray(max_pos, dtype=np.float64)
+        lib().gto_map_reset_range(self.h, _dp(a), _dp(b))
+
+    def set_update_range(self, min_pos, max_pos):
+        """SDFMap::setUpdateRange (sdf_map.cpp:244-264): the window of the NEXT update_esdf only (:366-367)."""
+        a, b = np.asarray(min_pos, dtype=np.float64), np.asarray(max_pos, dtype=np.float64)
+        lib().gto_map_set_update_range(self.h, _dp(a), _dp(b))
+
+    def update_range(self):
+        out = np.zeros(6, dtype=np.int32)
+        lib().gto_map_update_range(self.h, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out[:3].copy(), out[3:].copy()
 
     def set_occupancy(self, pts):
         p = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)

@@ -124,12 +124,14 @@ bool SDFMap::isInMap(const double pos[3]) const {  // :55-69
   return true;
 }
 
-void SDFMap::resetBuffer() {  // :26-53 with (min_range, max_range): whole grid
+void SDFMap::resetBuffer() { resetBuffer(min_range, max_range); }  // :26
+
+void SDFMap::resetBuffer(const double min_pos_in[3], const double max_pos_in[3]) {  // :28-53
   double min_pos[3], max_pos[3];
   int min_id[3], max_id[3];
   for (int i = 0; i < 3; ++i) {
-    min_pos[i] = std::max(min_range[i], min_range[i]);
-    max_pos[i] = std::min(max_range[i], max_range[i]) - resolution / 2;
+    min_pos[i] = std::max(min_pos_in[i], min_range[i]);
+    max_pos[i] = std::min(max_pos_in[i], max_range[i]) - resolution / 2;
   }
   posToIndex(min_pos, min_id);
   posToIndex(max_pos, max_id);
@@ -140,6 +142,16 @@ void SDFMap::resetBuffer() {  // :26-53 with (min_range, max_range): whole grid
         occupancy_buffer[a] = 0;
         distance_buffer[a] = 10000;
       }
+}
+
+void SDFMap::setUpdateRange(const double min_pos_in[3], const double max_pos_in[3]) {  // :244-264
+  double min_pos[3], max_pos[3];
+  for (int i = 0; i < 3; ++i) {
+    min_pos[i] = std::max(min_pos_in[i], min_range[i]);
+    max_pos[i] = std::min(max_pos_in[i], max_range[i]) - resolution / 2;
+  }
+  posToIndex(min_pos, min_vec);
+  posToIndex(max_pos, max_vec);
 }
 
 void SDFMap::setOccupancy(const double pos[3], int occ) {  // :80-99

@@ -76,6 +76,9 @@ class SDFMap {
  public:
   SDFMap(const double origin[3], double resolution, const double map_size[3]);
   void resetBuffer();
+  // windowed forms (sdf_map.cpp:28-53, :244-264): reset / restrict the next updateESDF3d to a box given in metres
+  void resetBuffer(const double min_pos[3], const double max_pos[3]);
+  void setUpdateRange(const double min_pos[3], const double max_pos[3]);
   void setOccupancy(const double pos[3], int occ = 1);
   void updateESDF3d();
   // brute-force O(N * N_occ) unsigned EDT, same output convention; self-check only.

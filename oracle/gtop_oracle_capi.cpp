@@ -34,6 +34,13 @@ void gto_map_grid(void* h, int out[3]) {
   for (int i = 0; i < 3; ++i) out[i] = ((SDFMap*)h)->grid_size[i];
 }
 void gto_map_reset(void* h) { ((SDFMap*)h)->resetBuffer(); }
+void gto_map_reset_range(void* h, const double* min_pos, const double* max_pos) { ((SDFMap*)h)->resetBuffer(min_pos, max_pos); }
+void gto_map_set_update_range(void* h, const double* min_pos, const double* max_pos) {
+  ((SDFMap*)h)->setUpdateRange(min_pos, max_pos);
+}
+void gto_map_update_range(void* h, int out[6]) {
+  for (int i = 0; i < 3; ++i) out[i] = ((SDFMap*)h)->min_vec[i], out[3 + i] = ((SDFMap*)h)->max_vec[i];
+}
 void gto_map_set_occupancy(void* h, const double* xyz, int64_t n) {
   SDFMap* m = (SDFMap*)h;
   for (int64_t i = 0; i < n; ++i) m->setOccupancy(xyz + 3 * i, 1);

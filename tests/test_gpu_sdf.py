@@ -135,3 +135,84 @@ def test_fast_integer_sqrt_is_correctly_rounded_everywhere(gtop_lib):
     bad = C.c_int64(-1)
     assert gtop_lib.gtop_debug_check_sqrt(3 * 8192 * 8192, C.byref(bad)) == 0
     assert bad.value == 0
+
+
+def _window_sequence(om, gm, steps):
+    """apply the same call sequence to the oracle map and the GPU map, comparing both buffers after every step"""
+    for k, (what, *args) in enumerate(steps):
+        getattr(om, what)(*args), getattr(gm, what)(*args)
+        assert np.array_equal(gm.occupancy(), om.occupancy()), "occupancy differs after step %d (%s)" % (k, what)
+        d_gpu, d_ref = gm.distance(), om.distance()
+        assert np.array_equal(d_gpu, d_ref), "distance differs after step %d (%s): %g" % (k, what, np.abs(d_gpu - d_ref).max())
+        lo, hi = gm.update_range()
+        olo, ohi = om.update_range()
+        assert np.array_equal(lo, olo) and np.array_equal(hi, ohi)
+
+
+@pytest.mark.parametrize("dims,res", [((40, 36, 20), 0.1), ((23, 17, 9), 0.25), ((150, 130, 140), 0.05)])
+def test_windowed_update_and_reset_bit_exact(gtop_lib, dims, res):
+    """setUpdateRange / resetBuffer(min,max) / updateESDF3d on a box (sdf_map.cpp:28-53, :244-264, :310-368): the GPU
+    map follows the oracle bit for bit through full and windowed updates, and the window resets after each update."""
+    origin = np.array([-2.0, 1.0, 0.0])
+    size = np.array(dims, dtype=np.float64) * res
+    rng = fx.Rng(11 + dims[0])
+    pts = origin + 1e-3 + rng.uniform((60, 3)) * (size - 2e-3)
+    more = origin + 1e-3 + rng.uniform((40, 3)) * (size - 2e-3)
+    a = origin + size * np.array([0.2, 0.3, 0.1])
+    b = origin + size * np.array([0.7, 0.9, 0.8])
+    c = origin + size * np.array([0.5, -1.0, 0.45])   # clamped on y-
+    d = origin + size * np.array([2.0, 0.6, 0.95])    # clamped on x+
+    om, gm = OracleMap(origin, res, size), _gpu_map(origin, res, size)
+    _window_sequence(om, gm, [
+        ("set_occupancy", pts), ("update_esdf",),                        # whole grid
+        ("set_occupancy", more), ("set_update_range", a, b), ("update_esdf",),   # only the box sees the new points
+        ("reset_range", c, d), ("set_update_range", c, d), ("update_esdf",),     # local rebuild
+        ("set_update_range", a, d), ("update_esdf",),
+        ("update_esdf",),                                                # whole grid again (:366-367)
+        ("reset",), ("set_occupancy", more), ("set_update_range", c, b), ("update_esdf",),  # window first after a reset
+    ])
+
+
+def test_windowed_update_empty_window_and_errors(gtop_lib):
+    from grad_traj_optimization_b200._capi import GtopError
+    origin, res, size = [0.0, 0.0, 0.0], 0.5, [8.0, 6.0, 4.0]
+    om, gm = OracleMap(origin, res, size), _gpu_map(origin, res, size)
+    _window_sequence(om, gm, [("set_occupancy", np.array([[1.1, 1.1, 0.6]])),
+                              ("set_update_range", [4.0, 3.0, 2.0], [7.0, 5.0, 3.9]), ("update_esdf",)])  # no obstacle inside
+    assert np.all(gm.distance() == 10000.0)
+    for bad in (([9.0, 0, 0], [10.0, 1, 1]), ([3.0, 3.0, 3.0], [2.0, 4.0, 3.5])):  # outside the map / inverted
+        with pytest.raises(GtopError):
+            gm.set_update_range(*bad)
+        with pytest.raises(GtopError):
+            gm.reset_range(*bad)
+    lo, hi = gm.update_range()
+    assert np.array_equal(lo, [0, 0, 0]) and np.array_equal(hi, [15, 11, 7])  # a rejected call leaves the window alone
+
+
+def test_windowed_update_keeps_the_gather_copy_in_step(gtop_lib):
+    """The evaluation kernels gather from the xy-quad copy of the distance buffer, which a windowed update / reset only
+    rebuilds around the box: evaluations on such a map equal those on a map that received the same distances whole."""
+    from grad_traj_optimization_b200 import api
+    cfg = fx.load_cfg("opti_node")
+    origin, res, size = cfg["map_origin"], cfg["resolution"], cfg["map_size"]
+    gm = _gpu_map(origin, res, size)
+    gm.update(cfg["obstacles"])
+    wp = np.asarray(cfg["waypoints"], dtype=np.float64)
+    lo = wp.min(axis=0) - 0.7
+    hi = wp.max(axis=0) + 0.4
+    extra = wp[1:-1] + np.array([0.35, -0.2, 0.1])
+    gm.reset_range(lo, wp.mean(axis=0))
+    gm.set_occupancy(extra)
+    gm.set_update_range(lo, hi)
+    gm.update_esdf()
+    ref = _gpu_map(origin, res, size)
+    ref.upload_distance(gm.distance())
+    ps = api.ProblemSet.from_paths(wp[None], api.make_params(cfg["params"]))
+    x0, (lb, ub) = ps.x0(), ps.bounds()
+    X = fx.multi_starts(x0[0], lb[0], ub[0], 64, seed=3)
+    c1, g1, _ = ps.eval_host(gm, X, step=2, starts_per_problem=64)
+    c2, g2, _ = ps.eval_host(ref, X, step=2, starts_per_problem=64)
+    assert np.array_equal(c1, c2) and np.array_equal(g1, g2)
+    c1, g1, _ = ps.eval_host(gm, X[:5], step=2, starts_per_problem=1)   # general kernel
+    c2, g2, _ = ps.eval_host(ref, X[:5], step=2, starts_per_problem=1)
+    assert np.array_equal(c1, c2) and np.array_equal(g1, g2)
