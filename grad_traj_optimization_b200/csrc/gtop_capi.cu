@@ -499,7 +499,18 @@ int gtop_sdf_query(const gtop_sdf* s, const double* pos, int64_t n, double* dist
 static int finish_problems(gtop_problems* p, gtop_problems** out) {
   const ProbLayout& L = p->layout;
   std::vector<double> rec((size_t)p->np * L.stride);
-  for (int i = 0; i < p->np; ++i) pack_record(p->host[i], rec.data() + (size_t)i * L.stride);
+  {  // independent records: pack them on all host threads
+    std::atomic<int> next(0);
+    auto work = [&]() {
+      for (int i; (i = next.fetch_add(1)) < p->np;) pack_record(p->host[i], rec.data() + (size_t)i * L.stride);
+    };
+    int nt = (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, p->np / 64));
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; ++i) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
   cudaError_t e = cudaMalloc(&p->rec, sizeof(double) * rec.size());
   if (e == cudaSuccess) e = cudaMemcpy(p->rec, rec.data(), sizeof(double) * rec.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&p->oob, sizeof(unsigned long long));
