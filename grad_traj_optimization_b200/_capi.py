@@ -17,7 +17,8 @@ SYMBOLS = (
     "gtop_sdf_set_occupancy", "gtop_sdf_set_occupancy_boxes", "gtop_sdf_update_esdf", "gtop_sdf_last_edt_ms",
     "gtop_sdf_download_distance", "gtop_sdf_upload_distance", "gtop_sdf_download_occupancy",
     "gtop_sdf_upload_occupancy", "gtop_sdf_distance_device_ptr", "gtop_sdf_query", "gtop_problems_create_dense",
-    "gtop_problems_create_from_paths", "gtop_problems_create_from_kino", "gtop_problems_destroy", "gtop_problems_dims", "gtop_problems_set_params",
+    "gtop_problems_create_from_paths", "gtop_problems_create_from_kino", "gtop_problems_create_from_paths_device",
+    "gtop_problems_create_from_kino_device", "gtop_problems_record", "gtop_problems_destroy", "gtop_problems_dims", "gtop_problems_set_params",
     "gtop_problems_seg_time", "gtop_problems_x0", "gtop_problems_bounds", "gtop_problems_dense_L",
     "gtop_problems_dense_R", "gtop_problems_Df", "gtop_eval_batch_device", "gtop_eval_batch_host",
     "gtop_problems_take_out_of_map", "gtop_kernel_launch_count", "gtop_coeff_from_x", "gtop_objective_ctx_create",
@@ -79,7 +80,10 @@ def lib():
         "gtop_sdf_query": (C.c_int, [vp, dp, i64, dp, dp, C.POINTER(i64)]),
         "gtop_problems_create_dense": (C.c_int, [i32, i32, dp, dp, dp, dp, pp, C.c_int, pvp]),
         "gtop_problems_create_from_paths": (C.c_int, [i32, i32, dp, pp, C.c_int, pvp]),
+        "gtop_problems_record": (C.c_int, [vp, i32, dp, i64, C.POINTER(i64)]),
         "gtop_problems_create_from_kino": (C.c_int, [i32, i32, dp, dp, dp, dp, pp, C.c_int, pvp]),
+        "gtop_problems_create_from_paths_device": (C.c_int, [i32, i32, dp, pp, C.c_int, pvp]),
+        "gtop_problems_create_from_kino_device": (C.c_int, [i32, i32, dp, dp, dp, dp, pp, C.c_int, pvp]),
         "gtop_problems_destroy": (C.c_int, [vp]),
         "gtop_problems_dims": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "gtop_problems_set_params": (C.c_int, [vp, pp]),

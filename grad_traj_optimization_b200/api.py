@@ -165,19 +165,21 @@ class ProblemSet:
         return cls(h, p, int(device))
 
     @classmethod
-    def from_paths(cls, waypoints, params, device=0):
-        """Native path: waypoints [num_problems, m+1, 3] (setPath, grad_traj_optimizer.cpp:67-110)."""
+    def from_paths(cls, waypoints, params, device=0, setup="host"):
+        """Native path: waypoints [num_problems, m+1, 3] (setPath, grad_traj_optimizer.cpp:67-110).
+        setup="device" builds the per-problem records with the set-up kernel instead of the host threads."""
         w = _f64(waypoints)
         if w.ndim == 2:
             w = w[None]
         np_, m = w.shape[0], w.shape[1] - 1
         p = params if isinstance(params, GtopParams) else make_params(params)
         h = C.c_void_p()
-        check(lib().gtop_problems_create_from_paths(np_, m, _dp(w), C.byref(p), int(device), C.byref(h)))
+        create = {"host": lib().gtop_problems_create_from_paths, "device": lib().gtop_problems_create_from_paths_device}[setup]
+        check(create(np_, m, _dp(w), C.byref(p), int(device), C.byref(h)))
         return cls(h, p, int(device))
 
     @classmethod
-    def from_kino(cls, pos, vel, acc, time, params, device=0):
+    def from_kino(cls, pos, vel, acc, time, params, device=0, setup="host"):
         """Front-end hand-off (setKinoPath, grad_traj_optimizer.cpp:35-65): pos/vel/acc [np, m+1, 3], time [np, m]."""
         t = _f64(time)
         t = t.reshape(-1, t.shape[-1])
@@ -185,8 +187,8 @@ class ProblemSet:
         P, V, A = (_f64(a, (np_, m + 1, 3)) for a in (pos, vel, acc))
         p = params if isinstance(params, GtopParams) else make_params(params)
         h = C.c_void_p()
-        check(lib().gtop_problems_create_from_kino(np_, m, _dp(P), _dp(V), _dp(A), _dp(t), C.byref(p), int(device),
-                                                   C.byref(h)))
+        create = {"host": lib().gtop_problems_create_from_kino, "device": lib().gtop_problems_create_from_kino_device}[setup]
+        check(create(np_, m, _dp(P), _dp(V), _dp(A), _dp(t), C.byref(p), int(device), C.byref(h)))
         return cls(h, p, int(device))
 
     def close(self):
@@ -195,6 +197,21 @@ class ProblemSet:
             self.h = None
 
     __del__ = close
+
+    def record(self, problem=0):
+        """The packed device record of one problem (inspection / tests)."""
+        n = C.c_int64(0)
+        check(lib().gtop_problems_record(self.h, int(problem), None, 0, C.byref(n)))
+        out = np.empty(n.value)
+        check(lib().gtop_problems_record(self.h, int(problem), _dp(out), n.value, None))
+        return out
+
+    def layout_offsets(self):
+        """Offsets (in doubles) of the first sections of a record: dt, ns, Linv, tt, Rc (csrc/gtop_types.cuh)."""
+        m, ns = self.m, int(self.params.samples_per_segment)
+        o = {"dt": 0, "ns": m, "Linv": 2 * m, "tt": 2 * m + 36 * m}
+        o["Rc"] = o["tt"] + 5 * m * ns
+        return o
 
     def set_params(self, params):
         p = params if isinstance(params, GtopParams) else make_params(params)

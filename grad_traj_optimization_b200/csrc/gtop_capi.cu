@@ -16,6 +16,7 @@
 #include "gtop_types.cuh"
 #include "mma_core.cuh"
 #include "problem_setup.hpp"
+#include "setup_core.cuh"
 
 namespace gtop {
 cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
@@ -32,6 +33,8 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
 cudaError_t launch_edt_window(const uint8_t* occ, uint8_t* wocc, int32_t* d1, int32_t* d2, double* wdist, double* dist,
                               const VoxelBox& b, int ny, int nz, double res, cudaStream_t st, cudaEvent_t* ev);
 cudaError_t launch_build_quads_box(const SdfView& S, const double* dist, void* quad, const VoxelBox& b, cudaStream_t st);
+cudaError_t launch_setup_problems(const ProbLayout& PL, double mean_v, double init_time, const double* pos_dev,
+                                  const double* time_dev, int np, double* rec_dev, int* status_dev, cudaStream_t st);
 cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, int ny, int nz, double dval, cudaStream_t st);
 cudaError_t measure_fp64_peak(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev, cudaStream_t st);
@@ -110,7 +113,12 @@ struct gtop_problems {
   int np = 0;
   ProbLayout layout{};
   gtop_params prm{};
-  std::vector<ProblemHost> host;
+  // host copies of the problems.  Sets created on the device (gtop_problems_create_*_device) only carry the cheap
+  // parts here (segment times, Df, x0, NLopt box); the per-segment blocks of problem i are set up on the host the
+  // first time an accessor needs them (dense_L / dense_R / coeff_from_x) from the retained inputs below.
+  mutable std::vector<ProblemHost> host;
+  bool device_setup = false;
+  std::vector<double> in_pos, in_vel, in_acc, in_time;  // inputs of a device set-up ([np][m+1][3], [np][m])
   double* rec = nullptr;               // np * layout.stride doubles
   unsigned long long* oob = nullptr;   // device counter
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};  // [0] compute (and default), [1] H2D, [2] D2H
@@ -496,6 +504,7 @@ int gtop_sdf_query(const gtop_sdf* s, const double* pos, int64_t n, double* dist
 }
 
 // ================================================================================ problems
+static int finish_handle(gtop_problems* p, cudaError_t e, gtop_problems** out);
 static int finish_problems(gtop_problems* p, gtop_problems** out) {
   const ProbLayout& L = p->layout;
   std::vector<double> rec((size_t)p->np * L.stride);
@@ -513,6 +522,11 @@ static int finish_problems(gtop_problems* p, gtop_problems** out) {
   }
   cudaError_t e = cudaMalloc(&p->rec, sizeof(double) * rec.size());
   if (e == cudaSuccess) e = cudaMemcpy(p->rec, rec.data(), sizeof(double) * rec.size(), cudaMemcpyHostToDevice);
+  return finish_handle(p, e, out);
+}
+
+// counters, streams and events of a problem set whose record is in place (or failed with `e`)
+static int finish_handle(gtop_problems* p, cudaError_t e, gtop_problems** out) {
   if (e == cudaSuccess) e = cudaMalloc(&p->oob, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(p->oob, 0, sizeof(unsigned long long));
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
@@ -615,6 +629,95 @@ int gtop_problems_create_from_kino(int32_t np, int32_t m, const double* pos, con
   return finish_problems(p, out);
 }
 
+// Set-up on the device (setup_kernels.cu): only the waypoints (and, for the kino form, the segment times) are uploaded.
+static int create_on_device(int32_t np, int32_t m, const double* pos, const double* vel, const double* acc,
+                            const double* time, const gtop_params* prm, int device, gtop_problems** out) {
+  if (int rc = check_params(prm)) return rc;
+  REQUIRE(time || prm->mean_v > 0.0, "mean_v must be > 0");
+  REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  gtop_problems* p = new gtop_problems();
+  p->device = device, p->np = np, p->prm = *prm, p->device_setup = true;
+  p->layout = make_layout(m, prm->samples_per_segment);
+  const ProbLayout& L = p->layout;
+  const size_t w = (size_t)(m + 1) * 3;
+  p->in_pos.assign(pos, pos + (size_t)np * w);
+  if (vel) p->in_vel.assign(vel, vel + (size_t)np * w);
+  if (acc) p->in_acc.assign(acc, acc + (size_t)np * w);
+  if (time) p->in_time.assign(time, time + (size_t)np * m);
+  // the cheap host parts: segment times (same IEEE operations as the kernel), Df, x0 and the NLopt box
+  p->host.resize(np);
+  for (int i = 0; i < np; ++i) {
+    ProblemHost& h = p->host[i];
+    const double* wp = pos + i * w;
+    h.m = m, h.ns_cap = prm->samples_per_segment;
+    h.seg_time.resize(m);
+    for (int s = 0; s < m; ++s) {
+      h.seg_time[s] = time ? time[(size_t)i * m + s] : setup_segment_time(wp, s, prm->mean_v, prm->init_time);
+      if (!(h.seg_time[s] > 0.0)) {
+        delete p;
+        return fail(GTOP_E_INVALID, "problem " + std::to_string(i) + ": non-positive segment time (coincident waypoints?)");
+      }
+    }
+    h.Df.assign(18, 0.0);
+    for (int a = 0; a < 3; ++a) h.Df[a * 6 + 0] = wp[a], h.Df[a * 6 + 3] = wp[3 * m + a];
+    h.x0.resize(L.n), h.lb.resize(L.n), h.ub.resize(L.n);
+    for (int a = 0; a < 3; ++a)
+      for (int q = 0; q < L.P; ++q)
+        setup_x0_box(wp, vel ? vel + i * w : nullptr, acc ? acc + i * w : nullptr, a, q, prm->bos, prm->vos, prm->aos,
+                     &h.x0[a * L.P + q], &h.lb[a * L.P + q], &h.ub[a * L.P + q]);
+    h.has_path = true;
+  }
+  double *d_pos = nullptr, *d_time = nullptr;
+  int* d_status = nullptr;
+  std::vector<int> status(np, 0);
+  cudaError_t e = cudaMalloc(&p->rec, sizeof(double) * (size_t)np * L.stride);
+  if (e == cudaSuccess) e = cudaMalloc(&d_pos, sizeof(double) * (size_t)np * w);
+  if (e == cudaSuccess && time) e = cudaMalloc(&d_time, sizeof(double) * (size_t)np * m);
+  if (e == cudaSuccess) e = cudaMalloc(&d_status, sizeof(int) * (size_t)np);
+  if (e == cudaSuccess) e = cudaMemcpy(d_pos, pos, sizeof(double) * (size_t)np * w, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && time) e = cudaMemcpy(d_time, time, sizeof(double) * (size_t)np * m, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_setup_problems(L, prm->mean_v, prm->init_time, d_pos, d_time, np, p->rec, d_status, nullptr);
+  ++g_launches;
+  if (e == cudaSuccess) e = cudaMemcpy(status.data(), d_status, sizeof(int) * (size_t)np, cudaMemcpyDeviceToHost);
+  cudaFree(d_pos), cudaFree(d_time), cudaFree(d_status);
+  if (e == cudaSuccess)
+    for (int i = 0; i < np; ++i)
+      if (status[i]) {
+        gtop_problems_destroy(p);
+        return fail(GTOP_E_INVALID, "problem " + std::to_string(i) + (status[i] == 2 ? ": singular segment mapping matrix"
+                                                                                    : ": non-positive segment time"));
+      }
+  return finish_handle(p, e, out);
+}
+
+int gtop_problems_create_from_paths_device(int32_t np, int32_t m, const double* waypoints, const gtop_params* prm,
+                                           int device, gtop_problems** out) {
+  REQUIRE(np >= 1 && m >= 2 && waypoints && out, "bad argument");
+  return create_on_device(np, m, waypoints, nullptr, nullptr, nullptr, prm, device, out);
+}
+
+int gtop_problems_create_from_kino_device(int32_t np, int32_t m, const double* pos, const double* vel, const double* acc,
+                                          const double* time, const gtop_params* prm, int device, gtop_problems** out) {
+  REQUIRE(np >= 1 && m >= 2 && pos && vel && acc && time && out, "bad argument");
+  return create_on_device(np, m, pos, vel, acc, time, prm, device, out);
+}
+
+// the per-segment blocks of problem i on the host (device-built sets set them up on first use)
+static int ensure_blocks(const gtop_problems* p, int i) {
+  if (!p->device_setup || !p->host[i].Linv.empty()) return GTOP_OK;
+  const int m = p->layout.m;
+  const size_t w = (size_t)(m + 1) * 3;
+  ProblemHost h;
+  const std::string err =
+      p->in_time.empty() ? setup_from_path(m, p->in_pos.data() + i * w, p->prm, h)
+                         : setup_from_kino(m, p->in_pos.data() + i * w, p->in_vel.data() + i * w, p->in_acc.data() + i * w,
+                                           p->in_time.data() + (size_t)i * m, p->prm, h);
+  if (!err.empty()) return fail(GTOP_E_INVALID, "problem " + std::to_string(i) + ": " + err);
+  p->host[i] = std::move(h);
+  return GTOP_OK;
+}
+
 int gtop_problems_destroy(gtop_problems* p) {
   if (!p) return GTOP_OK;
   cudaSetDevice(p->device);
@@ -669,11 +772,13 @@ int gtop_problems_bounds(const gtop_problems* p, double* lb, double* ub) {
 }
 int gtop_problems_dense_L(const gtop_problems* p, int32_t i, double* L) {
   REQUIRE(p && L && i >= 0 && i < p->np, "bad argument");
+  if (int rc = ensure_blocks(p, i)) return rc;
   dense_L(p->host[i], L);
   return GTOP_OK;
 }
 int gtop_problems_dense_R(const gtop_problems* p, int32_t i, double* R) {
   REQUIRE(p && R && i >= 0 && i < p->np, "bad argument");
+  if (int rc = ensure_blocks(p, i)) return rc;
   dense_R(p->host[i], R);
   return GTOP_OK;
 }
@@ -684,8 +789,20 @@ int gtop_problems_Df(const gtop_problems* p, int32_t i, double* Df) {
   return GTOP_OK;
 }
 
+int gtop_problems_record(const gtop_problems* p, int32_t i, double* rec, int64_t cap, int64_t* len) {
+  REQUIRE(p && i >= 0 && i < p->np, "bad argument");
+  const int64_t n = p->layout.stride;
+  if (len) *len = n;
+  if (!rec) return GTOP_OK;
+  REQUIRE(cap >= n, "record buffer too small");
+  CU(cudaSetDevice(p->device));
+  CU(cudaMemcpy(rec, p->rec + (size_t)i * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  return GTOP_OK;
+}
+
 int gtop_coeff_from_x(const gtop_problems* p, int32_t i, const double* x, double* coeff) {
   REQUIRE(p && x && coeff && i >= 0 && i < p->np, "bad argument");
+  if (int rc = ensure_blocks(p, i)) return rc;
   coeff_from_x(p->host[i], x, coeff);
   return GTOP_OK;
 }

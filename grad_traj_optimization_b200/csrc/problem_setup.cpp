@@ -5,60 +5,10 @@
 #include <cstring>
 
 #include "gtop_types.cuh"
+#include "setup_core.cuh"
 
 namespace gtop {
 
-namespace {
-
-int factorial(int x) {
-  int f = 1;
-  for (int i = 2; i <= x; ++i) f *= i;
-  return f;
-}
-
-// 6x6 inverse by partial-pivot LU (row-major a[r][c]).  Returns false when singular.
-bool invert6(const double A[36], double Inv[36]) {
-  double lu[36];
-  int perm[6];
-  std::memcpy(lu, A, sizeof(lu));
-  for (int i = 0; i < 6; ++i) perm[i] = i;
-  for (int k = 0; k < 6; ++k) {
-    int piv = k;
-    double best = std::fabs(lu[k * 6 + k]);
-    for (int i = k + 1; i < 6; ++i)
-      if (std::fabs(lu[i * 6 + k]) > best) best = std::fabs(lu[i * 6 + k]), piv = i;
-    if (best == 0.0) return false;
-    if (piv != k) {
-      for (int j = 0; j < 6; ++j) std::swap(lu[k * 6 + j], lu[piv * 6 + j]);
-      std::swap(perm[k], perm[piv]);
-    }
-    for (int i = k + 1; i < 6; ++i) {
-      if (lu[i * 6 + k] == 0.0) continue;
-      const double l = (lu[i * 6 + k] /= lu[k * 6 + k]);
-      for (int j = k + 1; j < 6; ++j) lu[i * 6 + j] -= l * lu[k * 6 + j];
-    }
-  }
-  for (int c = 0; c < 6; ++c) {
-    double y[6];
-    for (int i = 0; i < 6; ++i) {
-      double s = perm[i] == c ? 1.0 : 0.0;
-      for (int j = 0; j < i; ++j) s -= lu[i * 6 + j] * y[j];
-      y[i] = s;
-    }
-    for (int i = 5; i >= 0; --i) {
-      double s = y[i];
-      for (int j = i + 1; j < 6; ++j) s -= lu[i * 6 + j] * Inv[j * 6 + c];
-      Inv[i * 6 + c] = s / lu[i * 6 + i];
-    }
-  }
-  return true;
-}
-
-// reference local row order is [p0,pT,v0,vT,a0,aT] (qp_generator.cpp:187-192); natural order used
-// by the kernels is [p0,v0,a0,pT,vT,aT].
-inline int ref_row_of_natural(int r) { return r < 3 ? 2 * r : 2 * (r - 3) + 1; }
-
-}  // namespace
 
 void build_time_table(ProblemHost& p) {
   const int m = p.m, NS = p.ns_cap;
@@ -74,7 +24,7 @@ void build_time_table(ProblemHost& p) {
     for (double t = 1e-3; t < T && k < NS; t += dt, ++k) {
       double* tt = &p.tt[(size_t)s * 5 * NS];
       tt[k] = t;
-      for (int q = 2; q <= 5; ++q) tt[(size_t)(q - 1) * NS + k] = std::pow(t, q);  // :457-485, :549
+      for (int q = 2; q <= 5; ++q) tt[(size_t)(q - 1) * NS + k] = setup_pow(t, q);  // :457-485, :549
     }
     p.ns[s] = (double)k;
   }
@@ -148,77 +98,23 @@ static std::string setup_common(int m, const double* pos, const double* vel, con
   out.Mseg.assign((size_t)m * 36, 0.0);
   for (int s = 0; s < m; ++s) {
     const double T = out.seg_time[s];
-    double A[36] = {0}, Ainv[36], Q[36] = {0};
-    for (int i = 0; i < 3; ++i) {  // qp_generator.cpp:187-192
-      A[(2 * i) * 6 + i] = factorial(i);
-      for (int j = i; j < 6; ++j) A[(2 * i + 1) * 6 + j] = factorial(j) / factorial(j - i) * std::pow(T, j - i);
-    }
-    for (int i = 3; i < 6; ++i)  // :227-233 (integer prefactor, exact)
-      for (int j = 3; j < 6; ++j)
-        Q[i * 6 + j] = i * (i - 1) * (i - 2) * j * (j - 1) * (j - 2) / (i + j - 5) * std::pow(T, i + j - 5);
-    if (!invert6(A, Ainv)) return "singular segment mapping matrix";
-    double* Li = &out.Linv[(size_t)s * 36];
-    for (int i = 0; i < 6; ++i)
-      for (int r = 0; r < 6; ++r) Li[i * 6 + r] = Ainv[i * 6 + ref_row_of_natural(r)];
-    // M = (Ainv^T Q) Ainv in natural order
-    double T1[36];
-    for (int r = 0; r < 6; ++r)
-      for (int j = 0; j < 6; ++j) {
-        double acc = 0.0;
-        for (int i = 0; i < 6; ++i) acc += Li[i * 6 + r] * Q[i * 6 + j];
-        T1[r * 6 + j] = acc;
-      }
-    double* M = &out.Mseg[(size_t)s * 36];
-    for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 6; ++c) {
-        double acc = 0.0;
-        for (int j = 0; j < 6; ++j) acc += T1[r * 6 + j] * Li[j * 6 + c];
-        M[r * 6 + c] = acc;
-      }
+    if (!setup_segment_blocks(T, &out.Linv[(size_t)s * 36], &out.Mseg[(size_t)s * 36])) return "singular segment mapping matrix";
   }
   // R in waypoint order = sum of the segment forms scattered on (wp s, wp s+1)
-  auto Rw = [&](int u, int v) {
-    const int wu = u / 3, wv = v / 3, qu = u % 3, qv = v % 3;
-    double r = 0.0;
-    if (wu == wv) {
-      if (wu >= 1) r += out.Mseg[(size_t)(wu - 1) * 36 + (3 + qu) * 6 + 3 + qv];
-      if (wu <= m - 1) r += out.Mseg[(size_t)wu * 36 + qu * 6 + qv];
-    } else if (wv == wu + 1) {
-      r = out.Mseg[(size_t)wu * 36 + qu * 6 + 3 + qv];
-    } else if (wv == wu - 1) {
-      r = out.Mseg[(size_t)wv * 36 + (3 + qu) * 6 + qv];
-    }
-    return r;
-  };
   out.Rc.assign((size_t)nd * 9, 0.0);
   for (int v = 0; v < nd; ++v)
-    for (int j = 0; j < 9; ++j) {
-      const int u = 3 * (v / 3 - 1) + j;
-      if (u >= 0 && u < nd) out.Rc[(size_t)v * 9 + j] = Rw(u, v);
-    }
+    for (int j = 0; j < 9; ++j) out.Rc[(size_t)v * 9 + j] = setup_Rc_entry(out.Mseg.data(), m, v, j);
   out.Rg.assign((size_t)P * 9, 0.0);
-  for (int i = 0; i < P; ++i) {
-    const int w = i / 3 + 1, self = 3 * w + i % 3;
-    for (int j = 0; j < 9; ++j) {
-      const int nb = 3 * (w - 1) + j, wpn = nb / 3;
-      const bool fixed = (wpn == 0 || wpn == m);
-      out.Rg[(size_t)i * 9 + j] = fixed ? Rw(nb, self) : Rw(self, nb);
-    }
-  }
+  for (int i = 0; i < P; ++i)
+    for (int j = 0; j < 9; ++j) out.Rg[(size_t)i * 9 + j] = setup_Rg_entry(out.Mseg.data(), m, i, j);
   // Df / x0 (getInitialD, qp_generator.cpp:407-451 with the straight-line init :204-221, zero start
   // velocity / acceleration :83-85) and the NLopt box (grad_traj_optimizer.cpp:151-177)
   out.Df.assign(18, 0.0);
   for (int a = 0; a < 3; ++a) out.Df[a * 6 + 0] = wp[a], out.Df[a * 6 + 3] = wp[3 * m + a];
   out.x0.assign(n, 0.0), out.lb.assign(n, 0.0), out.ub.assign(n, 0.0);
   for (int a = 0; a < 3; ++a)
-    for (int i = 0; i < P; ++i) {
-      const int w = i / 3 + 1, q = i % 3;
-      const double c = wp[3 * w + a];
-      out.x0[a * P + i] = (q == 0) ? c : (q == 1 ? (vel ? vel[3 * w + a] : 0.0) : (acc ? acc[3 * w + a] : 0.0));
-      const double half = q == 0 ? prm.bos : (q == 1 ? prm.vos : prm.aos);
-      out.lb[a * P + i] = (q == 0 ? c : 0.0) - half;  // box centred on the path / on zero (:154-177)
-      out.ub[a * P + i] = (q == 0 ? c : 0.0) + half;
-    }
+    for (int i = 0; i < P; ++i)
+      setup_x0_box(wp, vel, acc, a, i, prm.bos, prm.vos, prm.aos, &out.x0[a * P + i], &out.lb[a * P + i], &out.ub[a * P + i]);
   out.has_path = true;
   build_time_table(out);
   return "";
@@ -233,11 +129,7 @@ std::string setup_from_path(int m, const double* wp, const gtop_params& prm, Pro
   out.ns_cap = prm.samples_per_segment;
   // time allocation (grad_traj_optimizer.cpp:73-81; init_time on the first segment only, H9)
   out.seg_time.assign(m, 0.0);
-  for (int i = 0; i < m; ++i) {
-    const double dx = wp[3 * i] - wp[3 * i + 3], dy = wp[3 * i + 1] - wp[3 * i + 4], dz = wp[3 * i + 2] - wp[3 * i + 5];
-    const double len = std::sqrt(dx * dx + dy * dy + dz * dz);
-    out.seg_time[i] = (i == 0) ? len / prm.mean_v + prm.init_time : len / prm.mean_v;
-  }
+  for (int i = 0; i < m; ++i) out.seg_time[i] = setup_segment_time(wp, i, prm.mean_v, prm.init_time);
   return setup_common(m, wp, nullptr, nullptr, prm, out);
 }
 
@@ -306,10 +198,7 @@ void pack_record(const ProblemHost& p, double* rec) {
       for (int g = 0; g < 8; ++g) {
         const int r = deriv_of_col(g, s);
         if (r < 0) continue;
-        double a = 0.0, b = 0.0;
-        for (int i = 0; i < 6; ++i) a += pw[i] * p.Linv[(size_t)s * 36 + i * 6 + r];
-        for (int i = 1; i < 6; ++i) b += (double)i * pw[i - 1] * p.Linv[(size_t)s * 36 + i * 6 + r];
-        pl[(4 * g + j) * 2] = p.dt[s] * a, pl[(4 * g + j) * 2 + 1] = p.dt[s] * b;
+        setup_basis_pair(pw, &p.Linv[(size_t)s * 36], r, p.dt[s], &pl[(4 * g + j) * 2], &pl[(4 * g + j) * 2 + 1]);
       }
     }
     for (int pp = 0; pp < 3; ++pp)

@@ -136,6 +136,17 @@ int gtop_problems_create_from_paths(int32_t num_problems, int32_t m, const doubl
 int gtop_problems_create_from_kino(int32_t num_problems, int32_t m, const double* pos, const double* vel,
                                    const double* acc, const double* time, const gtop_params* params, int device,
                                    gtop_problems** out);
+/* The same two set-ups run ON THE DEVICE, one CTA per problem (csrc/setup_kernels.cu): only the waypoints / times are
+ * uploaded and the per-problem records are written in place — for batches with one waypoint set per trajectory, where
+ * the host set-up above costs far more than evaluating the batch.  Same arithmetic as the host path (shared source,
+ * no FMA contraction) except pow(), which is correctly rounded on the device and libm's on the host (1 ulp apart in
+ * about 0.08 % of the calls): the records agree to rounding level (<= 1e-12 relative).  All accessors work; dense_L / dense_R /
+ * coeff_from_x set the requested problem up on the host on first use. */
+int gtop_problems_create_from_paths_device(int32_t num_problems, int32_t m, const double* waypoints,
+                                           const gtop_params* params, int device, gtop_problems** out);
+int gtop_problems_create_from_kino_device(int32_t num_problems, int32_t m, const double* pos, const double* vel,
+                                          const double* acc, const double* time, const gtop_params* params, int device,
+                                          gtop_problems** out);
 int gtop_problems_destroy(gtop_problems* p);
 int gtop_problems_dims(const gtop_problems* p, int32_t* num_problems, int32_t* m, int32_t* n /* = 9(m-1) */);
 int gtop_problems_set_params(gtop_problems* p, const gtop_params* params); /* weights / penalty constants only */
@@ -146,6 +157,9 @@ int gtop_problems_bounds(const gtop_problems* p, double* lb, double* ub);       
 /* dense views for API parity with getL()/getR()/Df (col-major, per problem); native path only */
 int gtop_problems_dense_L(const gtop_problems* p, int32_t problem, double* L);
 int gtop_problems_dense_R(const gtop_problems* p, int32_t problem, double* R);
+/* inspection: the packed device record of one problem (csrc/gtop_types.cuh, ProbLayout) copied to the host; *len = its
+ * length in doubles (rec may be NULL to query it) */
+int gtop_problems_record(const gtop_problems* p, int32_t problem, double* rec, int64_t cap, int64_t* len);
 int gtop_problems_Df(const gtop_problems* p, int32_t problem, double* Df /* 3x6 col-major */);
 
 /* ---------------------------------------------------------------- evaluation ---- */

@@ -26,7 +26,7 @@ def main():
     out = {}
     for rep in range(3):
         t0 = time.perf_counter()
-        ps = api.ProblemSet.from_paths(wps, prm) if not args.device_setup else api.ProblemSet.from_paths_device(wps, prm)
+        ps = api.ProblemSet.from_paths(wps, prm, setup="device" if args.device_setup else "host")
         out["from_paths_ms"] = (time.perf_counter() - t0) * 1e3
     X = ps.x0()
     Xd = torch.from_numpy(X).cuda()
@@ -41,7 +41,7 @@ def main():
         ps.eval_device(gm, Xd, Cd, Gd, starts_per_problem=1, stream=st.cuda_stream)
     e1.record(st)
     torch.cuda.synchronize()
-    out.update(m=args.m, sets=args.sets, eval_ms=e0.elapsed_time(e1) / 20, host_threads=os.cpu_count())
+    out.update(setup="device" if args.device_setup else "host", m=args.m, sets=args.sets, eval_ms=e0.elapsed_time(e1) / 20, host_threads=os.cpu_count())
     print(json.dumps(out))
 
 
