@@ -33,7 +33,8 @@
 //     latency hides behind the second half of the iteration.
 //   * The smoothness cost is accumulated from the gradient rows (d_u * (R d)_u) while they are formed;
 //     the rows of the fixed start / end state are added before / after the segment loop.
-//   * The boundary derivatives live in a three-waypoint ring per trajectory (shared memory independent of m).
+//   * The boundary derivatives live in a four-waypoint ring per trajectory (shared memory independent of m),
+//     refilled from x by cp.async one segment ahead.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -59,36 +60,41 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // per-warp shared memory, in doubles:
-//   ring [8][27]        boundary derivatives of THREE consecutive waypoints per trajectory, [slot][axis][p,v,a]
-//                       with slot = waypoint % 3: segment s needs waypoints s, s+1 for its coefficients and
-//                       s-1, s, s+1 for the smoothness rows of waypoint s, so waypoint s+1 is fetched from x at the
-//                       top of segment s into the slot waypoint s-2 leaves.  Independent of m (a full copy of x
-//                       was 8 x 9(m+1) doubles: 6.3 KB per warp at m = 10, 18 KB at m = 30); stride 27 is odd ->
-//                       the 8 trajectories of a warp sit in distinct banks
+//   ring [8][37]        boundary derivatives of FOUR consecutive waypoints per trajectory, [slot][axis][p,v,a] with
+//                       slot = waypoint % 4: segment s needs waypoints s, s+1 for its coefficients and s-1, s, s+1 for
+//                       the smoothness rows of waypoint s; waypoint s+2 is copied from x into the fourth slot with
+//                       cp.async WHILE segment s runs, so the read of x never stalls a warp.  Independent of m (a full
+//                       copy of x was 8 x 9(m+1) doubles: 6.3 KB per warp at m = 10, 18 KB at m = 30); stride 37 is
+//                       odd -> the 8 trajectories of a warp sit in distinct banks
 //   coef [8][15][2]     coefficient pairs of the current segment, 15 16-byte elements per trajectory:
 //                       per axis (c0,c1) (c2,c3) (c4,c5) (2c2,3c3) (4c4,5c5).  The 240-byte trajectory
 //                       stride puts the 8 trajectories of a warp in the 8 distinct 16-byte bank groups
 //                       both for the loads (fixed element) and the stores (element varies with the lane)
 //   scr  [8][9]         finished collision-gradient rows of one waypoint (3 axes x p,v,a)
-constexpr int kRing = 27;
+constexpr int kRing = 37;
 __host__ __device__ inline int mma_warp_smem_doubles() { return 8 * kRing + 240 + 72; }
 
 // coefficients c[a][i] = sum_r Linv[i][r] * dseg[a][r], summed in ascending dense-column order of L
 // (start derivatives first, except for the last segment whose end derivatives live in columns 3..5
-// of d) with unfused mul/add — the same 6-term sum as `L * d` (:273).  Work item = (axis, power pair).
+// of d) with unfused mul/add — the same 6-term sum as `L * d` (:273).  Lane j < 3 takes the power pair
+// (2j, 2j+1) of all three axes: its six Linv pairs are loaded once (3 distinct addresses per warp
+// instruction), and the four lanes of a trajectory read the same waypoint values (shared-memory broadcast).
 template <bool kLast>
 __device__ __forceinline__ void coef_phase(const double* __restrict__ wp0, const double* __restrict__ wp1,
                                            const double2* __restrict__ LiTP, double2* __restrict__ coef, int j) {
-  for (int item = j; item < 9; item += 4) {
-    const int a = item / 3, p = item - 3 * a;
+  if (j >= 3) return;
+  const int p = j;
+  double2 L[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) L[r] = ldg_tab(LiTP + p * 6 + r);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
     const double *ws = wp0 + 3 * a, *we = wp1 + 3 * a;  // (p,v,a) of the segment's start / end waypoint
-    const double2* wt = LiTP + p * 6;
     double q0[6], q1[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      const double2 L = ldg_tab(wt + r);
       const double w = r < 3 ? ws[r] : we[r - 3];
-      q0[r] = __dmul_rn(L.x, w), q1[r] = __dmul_rn(L.y, w);
+      q0[r] = __dmul_rn(L[r].x, w), q1[r] = __dmul_rn(L[r].y, w);
     }
     double c0, c1;
     if (kLast) {
@@ -140,18 +146,25 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   const double* __restrict__ pr = prob + pid * (int64_t)PL.stride;
   const double* __restrict__ x = X + b * n;
 
-  // ---- 1. boundary derivatives of waypoints 0 and 1 into the ring -----------------------------------------
-  // waypoint w: the fixed start / end state (Df) for w = 0 / m, the free derivatives x[a*P + 3(w-1) + q] otherwise
+  // ---- 1. boundary derivatives of waypoints 0, 1 (and 2, in flight) into the ring ------------------------------
+  // waypoint w: the fixed start / end state (Df) for w = 0 / m, the free derivatives x[a*P + 3(w-1) + q] otherwise;
+  // copied global -> shared with cp.async (no register staging, no stall until the values are needed)
   auto fetch_waypoint = [&](int w) {
-    double* dst = ring + (w % 3) * 9;
+    double* dst = ring + (w & 3) * 9;
     for (int i = j; i < 9; i += 4) {
       const int a = i / 3, q = i - 3 * a;
-      dst[i] = w == 0 ? pr[PL.off_Df + a * 6 + q] : (w == m ? pr[PL.off_Df + a * 6 + 3 + q] : x[a * P + 3 * (w - 1) + q]);
+      const double* src = w == 0 ? pr + PL.off_Df + a * 6 + q : (w == m ? pr + PL.off_Df + a * 6 + 3 + q : x + a * P + 3 * (w - 1) + q);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + i)), "l"(src)
+                   : "memory");
     }
+  };
+  auto fetch_wait = [&]() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
   };
   fetch_waypoint(0);
   fetch_waypoint(1);
-  __syncwarp();
+  fetch_wait();
 
   double Jc = 0.0, js = 0.0;
   // smoothness cost, rows of the fixed start waypoint (column band of R, :326-327): needs waypoints 0 and 1
@@ -172,13 +185,12 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   double* __restrict__ gout = grad_out + b * n;
 
   for (int s = 0; s < m; ++s) {
-    if (s >= 1) {  // waypoint s+1 replaces waypoint s-2 (last read by the combine step of segment s-1)
-      fetch_waypoint(s + 1);
-      __syncwarp();
-    }
-    const double* wpm = ring + ((s + 2) % 3) * 9;  // waypoint s-1 (s >= 1)
-    const double* wp0 = ring + (s % 3) * 9;        // waypoint s
-    const double* wp1 = ring + ((s + 1) % 3) * 9;  // waypoint s+1
+    if (s >= 1) fetch_wait();  // waypoint s+1, requested during segment s-1, has landed
+    // waypoint s+2 replaces waypoint s-2 (last read by the combine step of segment s-1) while this segment runs
+    if (s + 2 <= m) fetch_waypoint(s + 2);
+    const double* wpm = ring + ((s + 3) & 3) * 9;  // waypoint s-1 (s >= 1)
+    const double* wp0 = ring + (s & 3) * 9;        // waypoint s
+    const double* wp1 = ring + ((s + 1) & 3) * 9;  // waypoint s+1
     if (!E.skip_collision) {
       const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + s * 36);
       if (s == m - 1) coef_phase<true>(wp0, wp1, LiTP, coef, j);
@@ -300,21 +312,28 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
     __syncwarp();
     if (s >= 1) {
       // smoothness rows 2 Rfp' df + 2 Rpp dp (:330-332) from the band of R, combined with the collision
-      // rows and written out (:425-431): 9 values per trajectory over its 4 lanes.  The same row
-      // products give the interior rows of the smoothness cost d' R d (:326-327).
-      for (int o = j; o < 9; o += 4) {
-        const int a = o / 3, r = o - 3 * a, jj = 3 * (s - 1) + r;
+      // rows and written out (:425-431).  The same row products give the interior rows of the smoothness
+      // cost d' R d (:326-327).  Lane r = j < 3 takes derivative r of the three axes: one band row per lane,
+      // the window of the ring read as shared-memory broadcasts.
+      if (j < 3) {
+        const int r = j, jj = 3 * (s - 1) + r;
         const double* __restrict__ band = pr + PL.off_Rg + jj * 9;
-        double gs = 0.0;  // window = waypoints s-1, s, s+1 of axis a
+        double bnd[9];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) gs = fma(wpm[a * 3 + u], band[u], gs);
+        for (int u = 0; u < 9; ++u) bnd[u] = __ldg(band + u);
 #pragma unroll
-        for (int u = 0; u < 3; ++u) gs = fma(wp0[a * 3 + u], band[3 + u], gs);
+        for (int a = 0; a < 3; ++a) {
+          double gs = 0.0;  // window = waypoints s-1, s, s+1 of axis a
 #pragma unroll
-        for (int u = 0; u < 3; ++u) gs = fma(wp1[a * 3 + u], band[6 + u], gs);
-        js = fma(gs, wp0[a * 3 + r], js);
-        const double val = (E.ws * (2.0 * gs) + E.wc * scr[o]) + 1e-5;
-        if (live) gout[a * P + jj] = val;
+          for (int u = 0; u < 3; ++u) gs = fma(wpm[a * 3 + u], bnd[u], gs);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) gs = fma(wp0[a * 3 + u], bnd[3 + u], gs);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) gs = fma(wp1[a * 3 + u], bnd[6 + u], gs);
+          js = fma(gs, wp0[a * 3 + r], js);
+          const double val = (E.ws * (2.0 * gs) + E.wc * scr[a * 3 + r]) + 1e-5;
+          if (live) gout[a * P + jj] = val;
+        }
       }
       __syncwarp();
     }
@@ -328,8 +347,8 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   // the ring still holds after the last segment
   if (j < 3) {
     const double* __restrict__ band = pr + PL.off_Rc + (3 * m + j) * 9;  // band entries 0..5 <-> waypoints m-1, m
-    const double* wa = ring + ((m - 1) % 3) * 9;
-    const double* wb = ring + (m % 3) * 9;
+    const double* wa = ring + ((m - 1) & 3) * 9;
+    const double* wb = ring + (m & 3) * 9;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       double y = 0.0;
