@@ -172,7 +172,7 @@ template <bool kWarpUniform>
 __device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, double& gx, double& gy, double& gz) {
   double dx = c.dx, dy = c.dy;
   const bool any_special = kWarpUniform ? __any_sync(kFull, c.special) : c.special;
-  if (any_special) {
+  if (__builtin_expect(any_special, 0)) {
     dx = c.xlow ? 0.0 : dx;
     dy = c.ylow ? 0.0 : dy;
   }
@@ -189,7 +189,7 @@ __device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, doubl
   gy = fma(c.dz, f1 - f0, f0);                            // :232-233
   const double ex0 = fma(dy, e10 - e00, e00), ex1 = fma(dy, e11 - e01, e01);
   gx = fma(c.dz, ex1 - ex0, ex0);                         // :234-239
-  if (any_special) {
+  if (__builtin_expect(any_special, 0)) {
     dist = c.in_map ? dist : -1.0;                        // :187, H3
     gx = (c.in_map && !c.xlow) ? gx : 0.0;
     gy = (c.in_map && !c.ylow) ? gy : 0.0;
