@@ -198,6 +198,21 @@ class ProblemSet:
 
     __del__ = close
 
+    METRICS = ("time_sum", "length", "jerk", "mean_v", "max_v", "mean_a", "max_a", "acc_cost")
+
+    def traj_metrics_host(self, X, traj_offset=0, starts_per_problem=1):
+        """PolynomialTraj evaluation of a batch of variable vectors (opti_node.cpp:104-144): [B, 8] in METRICS order."""
+        X = _f64(X, (-1, self.n))
+        out = np.empty((X.shape[0], 8))
+        check(lib().gtop_traj_metrics_host(self.h, _dp(X), X.shape[0], int(traj_offset), int(starts_per_problem), _dp(out)))
+        return out
+
+    def traj_metrics_device(self, X, out, traj_offset=0, starts_per_problem=1, stream=None):
+        """Same with device-resident torch tensors X [B, n] and out [B, 8] (float64, contiguous)."""
+        check(lib().gtop_traj_metrics_device(self.h, X.data_ptr(), X.shape[0], int(traj_offset), int(starts_per_problem),
+                                             out.data_ptr(), stream))
+        return out
+
     def record(self, problem=0):
         """The packed device record of one problem (inspection / tests)."""
         n = C.c_int64(0)

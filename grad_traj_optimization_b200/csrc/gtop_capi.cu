@@ -35,6 +35,8 @@ cudaError_t launch_edt_window(const uint8_t* occ, uint8_t* wocc, int32_t* d1, in
 cudaError_t launch_build_quads_box(const SdfView& S, const double* dist, void* quad, const VoxelBox& b, cudaStream_t st);
 cudaError_t launch_setup_problems(const ProbLayout& PL, double mean_v, double init_time, const double* pos_dev,
                                   const double* time_dev, int np, double* rec_dev, int* status_dev, cudaStream_t st);
+cudaError_t launch_traj_metrics(const ProbLayout& PL, const double* prob, int num_problems, const double* X, int64_t B,
+                                int64_t traj_offset, int64_t starts_per_problem, double* out, cudaStream_t st);
 cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, int ny, int nz, double dval, cudaStream_t st);
 cudaError_t measure_fp64_peak(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev, cudaStream_t st);
@@ -826,6 +828,43 @@ int gtop_eval_batch_device(const gtop_sdf* sdf, const gtop_problems* pr, const d
   CU(launch_eval(sdf->view, pr->layout, pr->rec, pr->np, make_scalars(pr->prm, step), X, B, off, starts, cost, grad,
                  pr->oob, 0, st));
   ++g_launches;
+  return GTOP_OK;
+}
+
+// ================================================================================ post-hoc metrics
+int gtop_traj_metrics_device(const gtop_problems* pr, const double* X, int64_t B, int64_t off, int64_t starts,
+                             double* metrics, void* stream) {
+  REQUIRE(pr, "null problems");
+  REQUIRE(B >= 0 && starts >= 1, "bad batch shape");
+  if (B == 0) return GTOP_OK;
+  REQUIRE(X && metrics, "null device buffer");
+  CU(cudaSetDevice(pr->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : pr->streams[0];
+  CU(launch_traj_metrics(pr->layout, pr->rec, pr->np, X, B, off, starts, metrics, st));
+  ++g_launches;
+  return GTOP_OK;
+}
+
+int gtop_traj_metrics_host(const gtop_problems* pr, const double* X, int64_t B, int64_t off, int64_t starts,
+                           double* metrics) {
+  REQUIRE(pr, "null problems");
+  REQUIRE(B >= 0 && starts >= 1, "bad batch shape");
+  if (B == 0) return GTOP_OK;
+  REQUIRE(X && metrics, "null host buffer");
+  CU(cudaSetDevice(pr->device));
+  const int n = pr->layout.n;
+  double *dX = nullptr, *dM = nullptr;
+  cudaError_t e = cudaMalloc(&dX, sizeof(double) * (size_t)B * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dM, sizeof(double) * (size_t)B * GTOP_NUM_TRAJ_METRICS);
+  cudaStream_t st = pr->streams[0];
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dX, X, sizeof(double) * (size_t)B * n, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_traj_metrics(pr->layout, pr->rec, pr->np, dX, B, off, starts, dM, st);
+  ++g_launches;
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(metrics, dM, sizeof(double) * (size_t)B * GTOP_NUM_TRAJ_METRICS, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(dX), cudaFree(dM);
+  CU(e);
   return GTOP_OK;
 }
 

@@ -73,6 +73,7 @@ inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 
 //                        start-derivative columns of s+1.  Padding slots and columns 6, 7 are zero: they
 //                        contribute nothing.
 //   LiTP  [m][3][6][2]   (Linv[2p][r], Linv[2p+1][r]): coefficient step, two powers per 128-bit load
+//   T     [m]            segment times T_s (segment_time, grad_traj_optimizer.cpp:73-81): post-hoc metrics kernel
 struct ProbLayout {
   int m;       // segments
   int P;       // free derivatives per axis = 3(m-1)
@@ -80,7 +81,7 @@ struct ProbLayout {
   int ns_cap;  // samples_per_segment (table capacity)
   int nsp;     // ns_cap rounded up to a multiple of 4
   int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df, off_LinvT;
-  int off_LiTP, off_TQ, off_PL;
+  int off_LiTP, off_TQ, off_PL, off_T;
   int stride;
 };
 
@@ -110,6 +111,7 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   o = (o + 7) & ~7;
   L.off_TQ = o, o += m * (L.nsp / 4) * 24;
   L.off_PL = o, o += m * (L.nsp / 4) * 64;
+  L.off_T = o, o += m;
   L.stride = (o + 7) & ~7;  // keep every record 64-byte aligned
   return L;
 }

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(128) k_setup_problems(SetupArgs A) {
     // for (double t = 1e-3; t < T; t += dt)  (:353): sequential accumulation reproduced
     for (double t = 1e-3; t < T && k < NS; t += dt, ++k) tt[k] = t;
     dts[s] = dt, nss[s] = (double)k;
+    rec[L.off_T + s] = T;
   }
   __syncthreads();
   if (bad) {

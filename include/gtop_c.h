@@ -175,6 +175,19 @@ int gtop_eval_batch_device(const gtop_sdf* sdf, const gtop_problems* problems, c
 int gtop_eval_batch_host(const gtop_sdf* sdf, const gtop_problems* problems, const double* X, int64_t B,
                          int64_t traj_offset, int64_t starts_per_problem, int step, double* cost, double* grad,
                          int64_t* n_out_of_map);
+
+/* ---------------------------------------------------------------- post-hoc metrics ---- */
+/* What opti_node computes from one optimised trajectory through PolynomialTraj (src/opti_node.cpp:104-144,
+ * include/grad_traj_optimization/polynomial_traj.hpp:70-203), for a batch: per trajectory GTOP_NUM_TRAJ_METRICS doubles
+ *   [0] time_sum  [1] length (getTraj every 0.01 s + getLength)  [2] jerk (getJerk)  [3] mean_v  [4] max_v
+ *   [5] mean_a  [6] max_a (getMeanAndMaxVel / Acc, literal: evaluated at the segment duration)  [7] acc cost (getAccCost)
+ * from the variables X (B x n, as the optimiser returns them) and the problems' mapping blocks (getCoefficient). */
+#define GTOP_NUM_TRAJ_METRICS 8
+int gtop_traj_metrics_device(const gtop_problems* problems, const double* X_dev, int64_t B, int64_t traj_offset,
+                             int64_t starts_per_problem, double* metrics_dev /* B x 8 */, void* stream);
+int gtop_traj_metrics_host(const gtop_problems* problems, const double* X, int64_t B, int64_t traj_offset,
+                           int64_t starts_per_problem, double* metrics /* B x 8 */);
+
 /* cumulative out-of-map sample counter of the problems handle (reset on read) */
 int gtop_problems_take_out_of_map(gtop_problems* p, int64_t* n);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */

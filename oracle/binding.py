@@ -105,6 +105,7 @@ def lib():
         "gto_opt_solve": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_char_p, C.c_void_p, vp, dp, dp,
                                     C.POINTER(C.c_int)]),
         "gto_opt_cost_curve": (i64, [vp, dp, i64]),
+        "gto_traj_metrics": (i64, [dp, dp, C.c_int, dp, dp, i64]),
         "gto_hardware_threads": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
@@ -334,6 +335,26 @@ class OracleOptimizer:
         out = np.empty(n)
         lib().gto_opt_cost_curve(self.h, _dp(out), n)
         return out
+
+
+TRAJ_METRICS = ("time_sum", "length", "jerk", "mean_v", "max_v", "mean_a", "max_a", "acc_cost")
+
+
+def traj_metrics(coeff, seg_time, want_traj=False):
+    """PolynomialTraj evaluation as opti_node runs it (opti_node.cpp:104-144): coeff [m, 18] (getCoefficient), seg_time [m].
+    Returns the 8 metrics (TRAJ_METRICS order) and, optionally, the getTraj points [N, 3]."""
+    c = np.ascontiguousarray(coeff, dtype=np.float64)
+    t = np.ascontiguousarray(seg_time, dtype=np.float64)
+    m = t.size
+    assert c.shape == (m, 18)
+    out = np.empty(8)
+    if not want_traj:
+        lib().gto_traj_metrics(_dp(c), _dp(t), m, _dp(out), None, 0)
+        return out
+    cap = int(t.sum() / 0.01) + 8
+    traj = np.empty((cap, 3))
+    npts = lib().gto_traj_metrics(_dp(c), _dp(t), m, _dp(out), _dp(traj), cap)
+    return out, traj[:npts]
 
 
 def hardware_threads():

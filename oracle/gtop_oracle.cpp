@@ -744,3 +744,156 @@ int GradTrajOptimizer::optimizeTrajectory(int step_, const SolveOptions& so, con
 }
 
 }  // namespace gtop_oracle
+
+// =============================================================================================
+// PolynomialTraj (polynomial_traj.hpp)
+// =============================================================================================
+namespace gtop_oracle {
+
+void PolynomialTraj::reset() {  // :27-30
+  times.clear(), cxs.clear(), cys.clear(), czs.clear();
+  time_sum = 0.0, num_seg = 0;
+}
+
+void PolynomialTraj::addSegment(const std::vector<double>& cx, const std::vector<double>& cy, const std::vector<double>& cz,
+                                double t) {  // :32-35
+  cxs.push_back(cx), cys.push_back(cy), czs.push_back(cz), times.push_back(t);
+}
+
+void PolynomialTraj::init() {  // :37-43
+  num_seg = (int)times.size();
+  time_sum = 0.0;
+  for (size_t i = 0; i < times.size(); ++i) time_sum += times[i];
+}
+
+void PolynomialTraj::evaluate(double t, double pt[3]) const {  // :45-65
+  int idx = 0;
+  while (idx < num_seg - 1 && times[idx] <= t) {  // (the reference has no bound on idx — H16)
+    t -= times[idx];
+    ++idx;
+  }
+  const int order = (int)cxs[idx].size();
+  std::vector<double> tv(order);
+  for (int i = 0; i < order; ++i) tv[order - 1 - i] = std::pow(t, double(i));
+  pt[0] = pt[1] = pt[2] = 0.0;
+  for (int k = 0; k < order; ++k) pt[0] += tv[k] * cxs[idx][k], pt[1] += tv[k] * cys[idx][k], pt[2] += tv[k] * czs[idx][k];
+}
+
+const std::vector<double>& PolynomialTraj::getTraj() {  // :70-79
+  double eval_t = 0.0;
+  traj_vec3d.clear();
+  while (eval_t <= time_sum) {
+    double pt[3];
+    evaluate(eval_t, pt);
+    traj_vec3d.insert(traj_vec3d.end(), pt, pt + 3);
+    eval_t += 0.01;
+  }
+  return traj_vec3d;
+}
+
+double PolynomialTraj::getLength() {  // :81-91
+  length = 0.0;
+  for (size_t i = 1; i < traj_vec3d.size() / 3; ++i) {
+    const double dx = traj_vec3d[3 * i] - traj_vec3d[3 * i - 3], dy = traj_vec3d[3 * i + 1] - traj_vec3d[3 * i - 2],
+                 dz = traj_vec3d[3 * i + 2] - traj_vec3d[3 * i - 1];
+    length += std::sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  return length;
+}
+
+double PolynomialTraj::getAccCost() const {  // :95-107
+  double cost = 0.0;
+  const int order = (int)cxs[0].size();
+  for (size_t s = 0; s < times.size(); ++s) {
+    const double ux = 2 * cxs[s][order - 3], uy = 2 * cys[s][order - 3], uz = 2 * czs[s][order - 3];
+    cost += (ux * ux + uy * uy + uz * uz) * times[s];
+  }
+  return cost;
+}
+
+double PolynomialTraj::getJerk() const {  // :109-139
+  double jerk = 0.0;
+  for (size_t s = 0; s < times.size(); ++s) {
+    const int order = (int)cxs[s].size();
+    std::vector<double> cxv(order), cyv(order), czv(order);
+    for (int j = 0; j < order; ++j) cxv[j] = cxs[s][order - 1 - j], cyv[j] = cys[s][order - 1 - j], czv[j] = czs[s][order - 1 - j];
+    const double ts = times[s];
+    std::vector<double> mat((size_t)order * order, 0.0);
+    for (double i = 3; i < order; i += 1)
+      for (double j = 3; j < order; j += 1)
+        mat[(size_t)i * order + (size_t)j] = i * (i - 1) * (i - 2) * j * (j - 1) * (j - 2) * std::pow(ts, i + j - 5) / (i + j - 5);
+    auto quad = [&](const std::vector<double>& c) {
+      double q = 0.0;
+      for (int j = 0; j < order; ++j) {
+        double col = 0.0;
+        for (int i = 0; i < order; ++i) col += c[i] * mat[(size_t)i * order + j];
+        q += col * c[j];
+      }
+      return q;
+    };
+    jerk += quad(cxv);
+    jerk += quad(cyv);
+    jerk += quad(czv);
+  }
+  return jerk;
+}
+
+void PolynomialTraj::getMeanAndMaxVel(double& mean_v, double& max_v) const {  // :141-171
+  int num = 0;
+  mean_v = 0.0, max_v = -1.0;
+  for (size_t s = 0; s < times.size(); ++s) {
+    const int order = (int)cxs[s].size();
+    std::vector<double> vx(order - 1), vy(order - 1), vz(order - 1);
+    for (int i = 0; i < order - 1; ++i) {
+      vx[i] = double(i + 1) * cxs[s][order - 2 - i];
+      vy[i] = double(i + 1) * cys[s][order - 2 - i];
+      vz[i] = double(i + 1) * czs[s][order - 2 - i];
+    }
+    const double ts = times[s];
+    double eval_t = 0.0;
+    while (eval_t < ts) {
+      double v[3] = {0, 0, 0};
+      for (int i = 0; i < order - 1; ++i) {
+        const double tv = std::pow(ts, i);  // ts, not eval_t (:158 — H16)
+        v[0] += tv * vx[i], v[1] += tv * vy[i], v[2] += tv * vz[i];
+      }
+      const double vn = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      mean_v += vn;
+      if (vn > max_v) max_v = vn;
+      ++num;
+      eval_t += 0.01;
+    }
+  }
+  mean_v = mean_v / double(num);
+}
+
+void PolynomialTraj::getMeanAndMaxAcc(double& mean_a, double& max_a) const {  // :173-203
+  int num = 0;
+  mean_a = 0.0, max_a = -1.0;
+  for (size_t s = 0; s < times.size(); ++s) {
+    const int order = (int)cxs[s].size();
+    std::vector<double> ax(order - 2), ay(order - 2), az(order - 2);
+    for (int i = 0; i < order - 2; ++i) {
+      ax[i] = double((i + 2) * (i + 1)) * cxs[s][order - 3 - i];
+      ay[i] = double((i + 2) * (i + 1)) * cys[s][order - 3 - i];
+      az[i] = double((i + 2) * (i + 1)) * czs[s][order - 3 - i];
+    }
+    const double ts = times[s];
+    double eval_t = 0.0;
+    while (eval_t < ts) {
+      double a[3] = {0, 0, 0};
+      for (int i = 0; i < order - 2; ++i) {
+        const double tv = std::pow(ts, i);  // ts, not eval_t (:190 — H16)
+        a[0] += tv * ax[i], a[1] += tv * ay[i], a[2] += tv * az[i];
+      }
+      const double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      mean_a += an;
+      if (an > max_a) max_a = an;
+      ++num;
+      eval_t += 0.01;
+    }
+  }
+  mean_a = mean_a / double(num);
+}
+
+}  // namespace gtop_oracle

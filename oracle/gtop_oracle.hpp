@@ -161,4 +161,34 @@ class GradTrajOptimizer {
   void finishSetup(TrajectoryGenerator& gen);
 };
 
+// ---------------------------------------------------------------------------------------------
+// PolynomialTraj restatement (include/grad_traj_optimization/polynomial_traj.hpp): the post-hoc evaluation
+// opti_node runs on the optimised trajectory (src/opti_node.cpp:108-144).  Coefficients are stored in
+// DESCENDING powers per segment (opti_node reverses the rows of getCoefficient, :117-119).
+// Reference quirks reproduced (H16): getMeanAndMaxVel / getMeanAndMaxAcc evaluate their polynomials at the
+// segment DURATION ts for every step of eval_t (pow(ts, i), :170, :202), i.e. the end velocity / acceleration of
+// the segment weighted by its number of 0.01 s steps; evaluate() would index past the last segment for
+// t == time_sum (:47-50) — clamped here.
+// ---------------------------------------------------------------------------------------------
+class PolynomialTraj {
+ public:
+  void reset();
+  void addSegment(const std::vector<double>& cx, const std::vector<double>& cy, const std::vector<double>& cz, double t);
+  void init();
+  void evaluate(double t, double pt[3]) const;                  // :45-65
+  double getTimeSum() const { return time_sum; }
+  const std::vector<double>& getTraj();                         // :70-79, xyz triples every 0.01 s
+  double getLength();                                           // :81-91 (needs getTraj first)
+  double getAccCost() const;                                    // :95-107
+  double getJerk() const;                                       // :109-139
+  void getMeanAndMaxVel(double& mean_v, double& max_v) const;   // :141-171
+  void getMeanAndMaxAcc(double& mean_a, double& max_a) const;   // :173-203
+
+  std::vector<double> times;
+  std::vector<std::vector<double>> cxs, cys, czs;
+  double time_sum = 0.0, length = 0.0;
+  int num_seg = 0;
+  std::vector<double> traj_vec3d;
+};
+
 }  // namespace gtop_oracle

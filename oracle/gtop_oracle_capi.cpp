@@ -9,6 +9,8 @@
 
 #include "gtop_oracle.hpp"
 
+#include <algorithm>
+
 using namespace gtop_oracle;
 
 static thread_local std::string g_err;
@@ -206,6 +208,34 @@ int64_t gto_opt_cost_curve(void* h, double* out, int64_t cap) {
   int64_t n = (int64_t)g->vec_cost.size();
   for (int64_t i = 0; i < n && i < cap; ++i) out[i] = g->vec_cost[i];
   return n;
+}
+
+// PolynomialTraj as opti_node builds it (src/opti_node.cpp:108-144): coeff = getCoefficient (m x 18 row-major, ascending
+// powers per axis), reversed into descending order per segment.  out[8] = time_sum, length, jerk, mean_v, max_v, mean_a,
+// max_a, acc_cost; traj (optional, cap triples) receives getTraj(); returns the number of trajectory points.
+int64_t gto_traj_metrics(const double* coeff, const double* seg_time, int m, double* out, double* traj, int64_t cap) {
+  PolynomialTraj pt;
+  pt.reset();
+  for (int s = 0; s < m; ++s) {
+    std::vector<double> c[3];
+    for (int a = 0; a < 3; ++a) {
+      c[a].assign(coeff + (size_t)s * 18 + a * 6, coeff + (size_t)s * 18 + a * 6 + 6);
+      std::reverse(c[a].begin(), c[a].end());
+    }
+    pt.addSegment(c[0], c[1], c[2], seg_time[s]);
+  }
+  pt.init();
+  const std::vector<double>& tr = pt.getTraj();
+  const int64_t npts = (int64_t)tr.size() / 3;
+  if (traj)
+    for (int64_t i = 0; i < std::min<int64_t>(npts, cap) * 3; ++i) traj[i] = tr[i];
+  out[0] = pt.getTimeSum();
+  out[1] = pt.getLength();
+  out[2] = pt.getJerk();
+  pt.getMeanAndMaxVel(out[3], out[4]);
+  pt.getMeanAndMaxAcc(out[5], out[6]);
+  out[7] = pt.getAccCost();
+  return npts;
 }
 
 int gto_hardware_threads() { return (int)std::thread::hardware_concurrency(); }

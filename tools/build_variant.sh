@@ -13,4 +13,4 @@ for f in eval_kernel eval_mma_kernel; do
   nvcc $FLAGS "$@" -Xptxas -v -c $SRC/$f.cu -o $OUT/$TAG/$f.o 2> $OUT/$TAG/$f.ptxas.log
 done
 grep -h "Used\|spill" $OUT/$TAG/eval_mma_kernel.ptxas.log | tr '\n' ' '; echo
-nvcc $ARCH -shared -o $OUT/libgtop_$TAG.so $OUT/$TAG/eval_kernel.o $OUT/$TAG/eval_mma_kernel.o $SRC/eval_one_kernel.o $SRC/sdf_kernels.o $SRC/solve_kernels.o $SRC/setup_kernels.o $SRC/gtop_capi.o $SRC/problem_setup.o -cudart static
+nvcc $ARCH -shared -o $OUT/libgtop_$TAG.so $OUT/$TAG/eval_kernel.o $OUT/$TAG/eval_mma_kernel.o $SRC/eval_one_kernel.o $SRC/sdf_kernels.o $SRC/solve_kernels.o $SRC/setup_kernels.o $SRC/traj_metrics_kernels.o $SRC/gtop_capi.o $SRC/problem_setup.o -cudart static
