@@ -16,7 +16,7 @@ SYMBOLS = (
     "gtop_sdf_reset_range", "gtop_sdf_set_update_range", "gtop_sdf_update_range",
     "gtop_sdf_set_occupancy", "gtop_sdf_set_occupancy_boxes", "gtop_sdf_update_esdf", "gtop_sdf_last_edt_ms",
     "gtop_sdf_download_distance", "gtop_sdf_upload_distance", "gtop_sdf_download_occupancy",
-    "gtop_sdf_upload_occupancy", "gtop_sdf_distance_device_ptr", "gtop_sdf_query", "gtop_problems_create_dense",
+    "gtop_sdf_upload_occupancy", "gtop_sdf_distance_device_ptr", "gtop_sdf_query", "gtop_sdf_query_dynamic", "gtop_problems_create_dense",
     "gtop_problems_create_from_paths", "gtop_problems_create_from_kino", "gtop_problems_create_from_paths_device",
     "gtop_problems_create_from_kino_device", "gtop_problems_record", "gtop_traj_metrics_device", "gtop_traj_metrics_host", "gtop_problems_destroy", "gtop_problems_dims", "gtop_problems_set_params",
     "gtop_problems_seg_time", "gtop_problems_x0", "gtop_problems_bounds", "gtop_problems_dense_L",
@@ -78,6 +78,7 @@ def lib():
         "gtop_sdf_upload_occupancy": (C.c_int, [vp, C.POINTER(i32)]),
         "gtop_sdf_distance_device_ptr": (C.c_int, [vp, pvp]),
         "gtop_sdf_query": (C.c_int, [vp, dp, i64, dp, dp, C.POINTER(i64)]),
+        "gtop_sdf_query_dynamic": (C.c_int, [vp, dp, i32, C.c_double, dp, i64, dp, dp, dp]),
         "gtop_problems_create_dense": (C.c_int, [i32, i32, dp, dp, dp, dp, pp, C.c_int, pvp]),
         "gtop_problems_create_from_paths": (C.c_int, [i32, i32, dp, pp, C.c_int, pvp]),
         "gtop_problems_record": (C.c_int, [vp, i32, dp, i64, C.POINTER(i64)]),

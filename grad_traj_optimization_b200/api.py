@@ -138,6 +138,18 @@ class SdfMap:
         return dist, grad, int(oob.value)
 
 
+    def query_dynamic(self, pos, boxes, time):
+        """Batched EDTEnvironment::evaluateEDTWithGrad / evaluateCoarseEDT (edt_environment.cpp:75-137): static field
+        min'ed with constant-velocity boxes [nbox, 9] = (centre at t=0, velocity, edge lengths) at `time`.
+        Returns (dist[n], grad[n,3], coarse[n])."""
+        p = _f64(pos, (-1, 3))
+        b = _f64(boxes, (-1, 9))
+        dist, grad, coarse = np.empty(p.shape[0]), np.empty((p.shape[0], 3)), np.empty(p.shape[0])
+        check(lib().gtop_sdf_query_dynamic(self.h, _dp(b), b.shape[0], float(time), _dp(p), p.shape[0], _dp(dist),
+                                           _dp(grad), _dp(coarse)))
+        return dist, grad, coarse
+
+
 class ProblemSet:
     """A set of trajectory problems with the same segment count m, resident on one GPU."""
 

@@ -37,6 +37,8 @@ cudaError_t launch_setup_problems(const ProbLayout& PL, double mean_v, double in
                                   const double* time_dev, int np, double* rec_dev, int* status_dev, cudaStream_t st);
 cudaError_t launch_traj_metrics(const ProbLayout& PL, const double* prob, int num_problems, const double* X, int64_t B,
                                 int64_t traj_offset, int64_t starts_per_problem, double* out, cudaStream_t st);
+cudaError_t launch_query_dynamic(const SdfView& S, const double* boxes_dev, int nbox, double time, const double* pos_dev,
+                                 int64_t n, double* dist_dev, double* grad_dev, double* coarse_dev, cudaStream_t st);
 cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, int ny, int nz, double dval, cudaStream_t st);
 cudaError_t measure_fp64_peak(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev, cudaStream_t st);
@@ -502,6 +504,31 @@ int gtop_sdf_query(const gtop_sdf* s, const double* pos, int64_t n, double* dist
   cudaFree(dp), cudaFree(dd), cudaFree(dg), cudaFree(dc);
   CU(e);
   if (n_oob) *n_oob = (int64_t)hc;
+  return GTOP_OK;
+}
+
+int gtop_sdf_query_dynamic(const gtop_sdf* s, const double* boxes, int32_t nbox, double time, const double* pos, int64_t n,
+                           double* dist, double* grad, double* coarse) {
+  REQUIRE(s && n >= 0 && nbox >= 0 && (nbox == 0 || boxes) && (n == 0 || (pos && dist && grad)), "bad argument");
+  REQUIRE(nbox <= 1024, "at most 1024 boxes");
+  if (n == 0) return GTOP_OK;
+  CU(cudaSetDevice(s->device));
+  double *dp = nullptr, *dd = nullptr, *dg = nullptr, *dc = nullptr, *db = nullptr;
+  cudaError_t e = cudaMalloc(&dp, sizeof(double) * 3 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dd, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dg, sizeof(double) * 3 * n);
+  if (e == cudaSuccess && coarse) e = cudaMalloc(&dc, sizeof(double) * n);
+  if (e == cudaSuccess && nbox > 0) e = cudaMalloc(&db, sizeof(double) * 9 * nbox);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dp, pos, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess && nbox > 0) e = cudaMemcpyAsync(db, boxes, sizeof(double) * 9 * nbox, cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = launch_query_dynamic(s->view, db, nbox, time, dp, n, dd, dg, dc, s->stream);
+  ++g_launches;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dist, dd, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(grad, dg, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess && coarse) e = cudaMemcpyAsync(coarse, dc, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(dp), cudaFree(dd), cudaFree(dg), cudaFree(dc), cudaFree(db);
+  CU(e);
   return GTOP_OK;
 }
 

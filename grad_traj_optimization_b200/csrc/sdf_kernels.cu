@@ -643,6 +643,99 @@ __global__ void k_query(SdfView S, const double* __restrict__ pos, int64_t n, do
   grad[3 * i] = __dmul_rn(g0, S.res_inv);
 }
 
+// ---------------------------------------------------------------------------------------------
+// batched EDTEnvironment::evaluateEDTWithGrad (src/edt_environment.cpp:75-122): the static field min'ed,
+// at the eight corner voxels of the cell, with the distance to constant-velocity boxes at `time`
+// (distToBox :27-44, evaluateConstVel obj_predictor.h:57-66), then the reference's trilinear value and gradient.
+// Corner values go through getDistance(Vector3d) (sdf_map.cpp:155-164): -1 for a corner outside the map, not clamped.
+// getInterpolationData is absent from the reference and taken from getDistWithGradTrilinear (sdf_map.cpp:196-209).
+// boxes: nbox x 9 = centre at t = 0, velocity, full edge lengths.  Unfused, reference order: bit-identical to the oracle.
+__global__ void k_query_dynamic(SdfView S, const double* __restrict__ boxes, int nbox, double time,
+                                const double* __restrict__ pos, int64_t n, double* __restrict__ dist,
+                                double* __restrict__ grad, double* __restrict__ coarse) {
+  extern __shared__ double bx[];  // per box: min[3], max[3] at `time`
+  for (int e = threadIdx.x; e < nbox * 3; e += blockDim.x) {
+    const int b = e / 3, a = e - 3 * b;
+    const double c = __dadd_rn(boxes[9 * b + a], __dmul_rn(time, boxes[9 * b + 3 + a]));  // 1.0*c0 + pow(t,1)*c1
+    const double h = __dmul_rn(0.5, boxes[9 * b + 6 + a]);
+    bx[6 * b + a] = __dsub_rn(c, h), bx[6 * b + 3 + a] = __dadd_rn(c, h);
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto in_map = [&](double x, double y, double z) {
+    return !(x < S.lox || y < S.loy || z < S.loz || x > S.hix || y > S.hiy || z > S.hiz);
+  };
+  auto min_box = [&](double x, double y, double z) {  // minDistToAllBox (:61-73)
+    double best = 10000000.0;
+    for (int b = 0; b < nbox; ++b) {
+      const double* q = bx + 6 * b;
+      const double ax = (x >= q[0] && x <= q[3]) ? 0.0 : fmin(fabs(__dsub_rn(x, q[0])), fabs(__dsub_rn(x, q[3])));
+      const double ay = (y >= q[1] && y <= q[4]) ? 0.0 : fmin(fabs(__dsub_rn(y, q[1])), fabs(__dsub_rn(y, q[4])));
+      const double az = (z >= q[2] && z <= q[5]) ? 0.0 : fmin(fabs(__dsub_rn(z, q[2])), fabs(__dsub_rn(z, q[5])));
+      const double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
+      if (d < best) best = d;
+    }
+    return best;
+  };
+  auto voxel_value = [&](double x, double y, double z) {  // getDistance(Vector3d)
+    if (!in_map(x, y, z)) return -1.0;
+    const int vx = (int)floor(__dmul_rn(__dsub_rn(x, S.ox), S.res_inv)), vy = (int)floor(__dmul_rn(__dsub_rn(y, S.oy), S.res_inv)),
+              vz = (int)floor(__dmul_rn(__dsub_rn(z, S.oz), S.res_inv));
+    return S.dist[((int64_t)vx * S.ny + vy) * S.nz + vz];
+  };
+  const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
+  if (coarse) {  // evaluateCoarseEDT (:124-137)
+    const double d1 = voxel_value(px, py, pz);
+    coarse[i] = time < 0.0 ? d1 : fmin(d1, min_box(px, py, pz));
+  }
+  const double fx = floor(__dmul_rn(__dsub_rn(__dsub_rn(px, S.half_res), S.ox), S.res_inv));
+  const double fy = floor(__dmul_rn(__dsub_rn(__dsub_rn(py, S.half_res), S.oy), S.res_inv));
+  const double fz = floor(__dmul_rn(__dsub_rn(__dsub_rn(pz, S.half_res), S.oz), S.res_inv));
+  const double dx = __dmul_rn(__dsub_rn(px, __dadd_rn(__dmul_rn(__dadd_rn(fx, 0.5), S.res), S.ox)), S.res_inv);
+  const double dy = __dmul_rn(__dsub_rn(py, __dadd_rn(__dmul_rn(__dadd_rn(fy, 0.5), S.res), S.oy)), S.res_inv);
+  const double dz = __dmul_rn(__dsub_rn(pz, __dadd_rn(__dmul_rn(__dadd_rn(fz, 0.5), S.res), S.oz)), S.res_inv);
+  double v[2][2][2];
+#pragma unroll
+  for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+      for (int cz = 0; cz < 2; ++cz) {
+        // corner position = indexToPos(idx + corner) (:76-78)
+        const double qx = __dadd_rn(__dmul_rn(__dadd_rn(fx + cx, 0.5), S.res), S.ox);
+        const double qy = __dadd_rn(__dmul_rn(__dadd_rn(fy + cy, 0.5), S.res), S.oy);
+        const double qz = __dadd_rn(__dmul_rn(__dadd_rn(fz + cz, 0.5), S.res), S.oz);
+        const double d1 = voxel_value(qx, qy, qz);
+        v[cx][cy][cz] = time < 0.0 ? d1 : fmin(d1, min_box(qx, qy, qz));
+      }
+  const double ex = __dsub_rn(1.0, dx), ey = __dsub_rn(1.0, dy), ez = __dsub_rn(1.0, dz);
+  const double v00 = __dadd_rn(__dmul_rn(ex, v[0][0][0]), __dmul_rn(dx, v[1][0][0]));
+  const double v01 = __dadd_rn(__dmul_rn(ex, v[0][0][1]), __dmul_rn(dx, v[1][0][1]));
+  const double v10 = __dadd_rn(__dmul_rn(ex, v[0][1][0]), __dmul_rn(dx, v[1][1][0]));
+  const double v11 = __dadd_rn(__dmul_rn(ex, v[0][1][1]), __dmul_rn(dx, v[1][1][1]));
+  const double v0 = __dadd_rn(__dmul_rn(ey, v00), __dmul_rn(dy, v10));
+  const double v1 = __dadd_rn(__dmul_rn(ey, v01), __dmul_rn(dy, v11));
+  dist[i] = __dadd_rn(__dmul_rn(ez, v0), __dmul_rn(dz, v1));
+  grad[3 * i + 2] = __dmul_rn(__dsub_rn(v1, v0), S.res_inv);
+  grad[3 * i + 1] = __dmul_rn(__dadd_rn(__dmul_rn(ez, __dsub_rn(v10, v00)), __dmul_rn(dz, __dsub_rn(v11, v01))), S.res_inv);
+  double g0 = __dmul_rn(__dmul_rn(ez, ey), __dsub_rn(v[1][0][0], v[0][0][0]));
+  g0 = __dadd_rn(g0, __dmul_rn(__dmul_rn(ez, dy), __dsub_rn(v[1][1][0], v[0][1][0])));
+  g0 = __dadd_rn(g0, __dmul_rn(__dmul_rn(dz, ey), __dsub_rn(v[1][0][1], v[0][0][1])));
+  g0 = __dadd_rn(g0, __dmul_rn(__dmul_rn(dz, dy), __dsub_rn(v[1][1][1], v[0][1][1])));
+  grad[3 * i] = __dmul_rn(g0, S.res_inv);
+}
+
+cudaError_t launch_query_dynamic(const SdfView& S, const double* boxes_dev, int nbox, double time, const double* pos_dev,
+                                 int64_t n, double* dist_dev, double* grad_dev, double* coarse_dev, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const size_t smem = sizeof(double) * 6 * (size_t)(nbox > 0 ? nbox : 1);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  k_query_dynamic<<<(unsigned)((n + 255) / 256), 256, smem, st>>>(S, boxes_dev, nbox, time, pos_dev, n, dist_dev, grad_dev,
+                                                                  coarse_dev);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_query(const SdfView& S, const double* pos_dev, int64_t n, double* dist_dev, double* grad_dev,
                          unsigned long long* oob_dev, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;

@@ -115,6 +115,13 @@ int gtop_sdf_distance_device_ptr(const gtop_sdf* sdf, const double** dev_ptr);
  * the out-of-map count through *n_out_of_map (nullable) */
 int gtop_sdf_query(const gtop_sdf* sdf, const double* pos /* n x 3 */, int64_t n, double* dist, double* grad /* n x 3 */,
                    int64_t* n_out_of_map);
+/* EDTEnvironment::evaluateEDTWithGrad / evaluateCoarseEDT (src/edt_environment.cpp:75-137) for n points: the static
+ * field min'ed at the eight corner voxels of the cell with the distance to nbox constant-velocity boxes at `time`
+ * (time < 0: static field only).  boxes: nbox x 9 = centre at t = 0, velocity, full edge lengths
+ * (PolynomialPrediction::evaluateConstVel + ObjScale, obj_predictor.h:57-66).  Corner voxels outside the map contribute
+ * -1 (getDistance(Vector3d), sdf_map.cpp:155-164), they are not clamped.  coarse may be NULL.  Host buffers. */
+int gtop_sdf_query_dynamic(const gtop_sdf* sdf, const double* boxes, int32_t nbox, double time, const double* pos /* n x 3 */,
+                           int64_t n, double* dist, double* grad /* n x 3 */, double* coarse);
 
 /* ---------------------------------------------------------------- problems ---- */
 /* Drop-in path: take the matrices the reference's setPath leaves in the optimizer.

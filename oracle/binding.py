@@ -106,6 +106,7 @@ def lib():
                                     C.POINTER(C.c_int)]),
         "gto_opt_cost_curve": (i64, [vp, dp, i64]),
         "gto_traj_metrics": (i64, [dp, dp, C.c_int, dp, dp, i64]),
+        "gto_edt_env_query": (None, [vp, dp, C.c_int, dp, i64, C.c_double, dp, dp, dp]),
         "gto_hardware_threads": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
@@ -182,6 +183,15 @@ class OracleMap:
         o = np.ascontiguousarray(occ, dtype=np.int32).reshape(-1)
         assert o.size == self.nvox
         lib().gto_map_set_occupancy_buffer(self.h, o.ctypes.data_as(C.POINTER(C.c_int32)))
+
+    def query_dynamic(self, pos, boxes, time):
+        """EDTEnvironment::evaluateEDTWithGrad / evaluateCoarseEDT (edt_environment.cpp:75-137): boxes [nbox, 9] =
+        (c0, c1, scale) of constant-velocity boxes.  Returns (dist[n], grad[n,3], coarse[n])."""
+        p = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 9)
+        dist, grad, coarse = np.empty(p.shape[0]), np.empty((p.shape[0], 3)), np.empty(p.shape[0])
+        lib().gto_edt_env_query(self.h, _dp(b), b.shape[0], _dp(p), p.shape[0], float(time), _dp(dist), _dp(grad), _dp(coarse))
+        return dist, grad, coarse
 
     def brute_edt(self):
         out = np.empty(self.nvox, dtype=np.float64)

@@ -162,6 +162,13 @@ void SDFMap::setOccupancy(const double pos[3], int occ) {  // :80-99
   occupancy_buffer[(size_t)id[0] * grid_size[1] * grid_size[2] + (size_t)id[1] * grid_size[2] + id[2]] = occ;
 }
 
+double SDFMap::getDistance(const double pos[3]) const {  // :155-164
+  if (!isInMap(pos)) return -1;
+  int id[3];
+  posToIndex(pos, id);
+  return distance_buffer[(size_t)id[0] * grid_size[1] * grid_size[2] + (size_t)id[1] * grid_size[2] + id[2]];
+}
+
 double SDFMap::getDistance(int x, int y, int z) const {  // :166-183 (clamped)
   x = std::max(std::min(x, grid_size[0] - 1), 0);
   y = std::max(std::min(y, grid_size[1] - 1), 0);
@@ -894,6 +901,80 @@ void PolynomialTraj::getMeanAndMaxAcc(double& mean_a, double& max_a) const {  //
     }
   }
   mean_a = mean_a / double(num);
+}
+
+}  // namespace gtop_oracle
+
+// =============================================================================================
+// EDTEnvironment (edt_environment.cpp)
+// =============================================================================================
+namespace gtop_oracle {
+
+double EDTEnvironment::distToBox(int idx, const double pos[3], double time) const {  // :27-44
+  const MovingBox& b = boxes_[idx];
+  double d[3];
+  for (int i = 0; i < 3; ++i) {
+    const double pos_box = 1.0 * b.c0[i] + std::pow(time, 1) * b.c1[i];  // evaluateConstVel (obj_predictor.h:57-66)
+    const double box_max = pos_box + 0.5 * b.scale[i];
+    const double box_min = pos_box - 0.5 * b.scale[i];
+    d[i] = pos[i] >= box_min && pos[i] <= box_max ? 0.0 : std::min(std::fabs(pos[i] - box_min), std::fabs(pos[i] - box_max));
+  }
+  return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+}
+
+double EDTEnvironment::minDistToAllBox(const double pos[3], double time) const {  // :61-73
+  double dist = 10000000.0;
+  for (size_t i = 0; i < boxes_.size(); i++) {
+    const double di = distToBox((int)i, pos, time);
+    if (di < dist) dist = di;
+  }
+  return dist;
+}
+
+void EDTEnvironment::evaluateEDTWithGrad(const double pos[3], double time, double& dist, double grad[3]) const {  // :75-122
+  // SDFMap::getInterpolationData (absent from the reference; restated from sdf_map.cpp:196-209)
+  const SDFMap& M = *sdf_map_;
+  double pos_m[3], idx_pos[3], diff[3];
+  int idx[3];
+  for (int i = 0; i < 3; ++i) pos_m[i] = pos[i] - 0.5 * M.resolution * 1.0;
+  M.posToIndex(pos_m, idx);
+  for (int i = 0; i < 3; ++i) idx_pos[i] = (idx[i] + 0.5) * M.resolution + M.origin[i];
+  for (int i = 0; i < 3; ++i) diff[i] = (pos[i] - idx_pos[i]) * M.resolution_inv;
+  double values[2][2][2];
+  for (int x = 0; x < 2; x++)
+    for (int y = 0; y < 2; y++)
+      for (int z = 0; z < 2; z++) {
+        const int c[3] = {idx[0] + x, idx[1] + y, idx[2] + z};
+        double pt[3];
+        for (int i = 0; i < 3; ++i) pt[i] = (c[i] + 0.5) * M.resolution + M.origin[i];  // indexToPos
+        const double d1 = M.getDistance(pt);
+        if (time < 0.0) {
+          values[x][y][z] = d1;
+        } else {
+          const double d2 = minDistToAllBox(pt, time);
+          values[x][y][z] = std::min(d1, d2);
+        }
+      }
+  const double v00 = (1 - diff[0]) * values[0][0][0] + diff[0] * values[1][0][0];
+  const double v01 = (1 - diff[0]) * values[0][0][1] + diff[0] * values[1][0][1];
+  const double v10 = (1 - diff[0]) * values[0][1][0] + diff[0] * values[1][1][0];
+  const double v11 = (1 - diff[0]) * values[0][1][1] + diff[0] * values[1][1][1];
+  const double v0 = (1 - diff[1]) * v00 + diff[1] * v10;
+  const double v1 = (1 - diff[1]) * v01 + diff[1] * v11;
+  dist = (1 - diff[2]) * v0 + diff[2] * v1;
+  grad[2] = (v1 - v0) * resolution_inv_;
+  grad[1] = ((1 - diff[2]) * (v10 - v00) + diff[2] * (v11 - v01)) * resolution_inv_;
+  grad[0] = (1 - diff[2]) * (1 - diff[1]) * (values[1][0][0] - values[0][0][0]);
+  grad[0] += (1 - diff[2]) * diff[1] * (values[1][1][0] - values[0][1][0]);
+  grad[0] += diff[2] * (1 - diff[1]) * (values[1][0][1] - values[0][0][1]);
+  grad[0] += diff[2] * diff[1] * (values[1][1][1] - values[0][1][1]);
+  grad[0] *= resolution_inv_;
+}
+
+double EDTEnvironment::evaluateCoarseEDT(const double pos[3], double time) const {  // :124-137
+  const double d1 = sdf_map_->getDistance(pos);
+  if (time < 0.0) return d1;
+  return std::min(d1, minDistToAllBox(pos, time));
 }
 
 }  // namespace gtop_oracle

@@ -84,6 +84,7 @@ class SDFMap {
   // brute-force O(N * N_occ) unsigned EDT, same output convention; self-check only.
   void bruteForceEDT(std::vector<double>& out) const;
   double getDistance(int x, int y, int z) const;  // clamped
+  double getDistance(const double pos[3]) const;  // :155-164: -1 outside the map, else the voxel's value
   // returns dist; grad set to 0 and *in_map=false when outside (H3 ruling)
   double getDistWithGradTrilinear(const double pos[3], double grad[3], bool* in_map) const;
   bool isInMap(const double pos[3]) const;
@@ -95,8 +96,10 @@ class SDFMap {
   std::vector<int> occupancy_buffer;
   std::vector<double> distance_buffer, tmp_buffer1, tmp_buffer2;
 
- private:
+ public:
   void posToIndex(const double pos[3], int id[3]) const;
+
+ private:
   template <typename FG, typename FS>
   void fillESDF(FG f_get_val, FS f_set_val, int start, int end, int dim);
 };
@@ -189,6 +192,36 @@ class PolynomialTraj {
   double time_sum = 0.0, length = 0.0;
   int num_seg = 0;
   std::vector<double> traj_vec3d;
+};
+
+// ---------------------------------------------------------------------------------------------
+// EDTEnvironment restatement (src/edt_environment.cpp, include/.../edt_environment.h; moving boxes from
+// obj_predictor.h:57-66): the static ESDF min'ed, at the eight corners of the trilinear cell, with the distance to
+// constant-velocity boxes at time `time` (:75-122).  PARITY UNPINNED and the callee is absent: the file is not
+// compiled by the reference's CMakeLists (:65-73) and calls SDFMap::getInterpolationData, which the reference's
+// sdf_map.h does not declare; it is restated here from its sibling getDistWithGradTrilinear (sdf_map.cpp:196-209:
+// pos_m = pos - res/2, idx = posToIndex(pos_m), diff = (pos - indexToPos(idx)) * res_inv, corner positions
+// indexToPos(idx + {0,1}^3)).  Corner values go through getDistance(Vector3d) (:155-164): -1 outside the map (NOT
+// clamped, unlike getDistWithGradTrilinear).
+// ---------------------------------------------------------------------------------------------
+struct MovingBox {
+  double c0[3], c1[3];  // PolynomialPrediction::evaluateConstVel: centre(t) = c0 + t * c1 (obj_predictor.h:57-66)
+  double scale[3];      // ObjScale: full edge lengths
+};
+
+class EDTEnvironment {
+ public:
+  void setMap(const SDFMap* map) { sdf_map_ = map, resolution_inv_ = 1 / map->resolution; }  // :11-15
+  void setObjects(const std::vector<MovingBox>& boxes) { boxes_ = boxes; }                    // :17-25
+  double distToBox(int idx, const double pos[3], double time) const;                          // :27-44
+  double minDistToAllBox(const double pos[3], double time) const;                             // :61-73
+  void evaluateEDTWithGrad(const double pos[3], double time, double& dist, double grad[3]) const;  // :75-122
+  double evaluateCoarseEDT(const double pos[3], double time) const;                           // :124-137
+
+ private:
+  const SDFMap* sdf_map_ = nullptr;
+  std::vector<MovingBox> boxes_;
+  double resolution_inv_ = 0.0;
 };
 
 }  // namespace gtop_oracle

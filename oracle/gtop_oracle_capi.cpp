@@ -238,6 +238,21 @@ int64_t gto_traj_metrics(const double* coeff, const double* seg_time, int m, dou
   return npts;
 }
 
+// EDTEnvironment::evaluateEDTWithGrad / evaluateCoarseEDT for n query points; boxes: nbox x 9 (c0[3], c1[3], scale[3])
+void gto_edt_env_query(void* map, const double* boxes, int nbox, const double* pos, int64_t n, double time, double* dist,
+                       double* grad, double* coarse) {
+  EDTEnvironment env;
+  env.setMap((SDFMap*)map);
+  std::vector<MovingBox> bx(nbox);
+  for (int i = 0; i < nbox; ++i)
+    for (int k = 0; k < 3; ++k) bx[i].c0[k] = boxes[9 * i + k], bx[i].c1[k] = boxes[9 * i + 3 + k], bx[i].scale[k] = boxes[9 * i + 6 + k];
+  env.setObjects(bx);
+  for (int64_t i = 0; i < n; ++i) {
+    env.evaluateEDTWithGrad(pos + 3 * i, time, dist[i], grad + 3 * i);
+    if (coarse) coarse[i] = env.evaluateCoarseEDT(pos + 3 * i, time);
+  }
+}
+
 int gto_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -216,3 +216,23 @@ def test_windowed_update_keeps_the_gather_copy_in_step(gtop_lib):
     c1, g1, _ = ps.eval_host(gm, X[:5], step=2, starts_per_problem=1)   # general kernel
     c2, g2, _ = ps.eval_host(ref, X[:5], step=2, starts_per_problem=1)
     assert np.array_equal(c1, c2) and np.array_equal(g1, g2)
+
+
+@pytest.mark.parametrize("time", [-1.0, 0.0, 0.8, 2.5])
+def test_dynamic_box_query_bit_exact(gtop_lib, time):
+    """EDTEnvironment::evaluateEDTWithGrad / evaluateCoarseEDT (edt_environment.cpp:75-137) against the oracle
+    restatement, including cells whose corner voxels lie outside the map (-1, not clamped)."""
+    cfg = fx.load_cfg("opti_node")
+    om = oracle_map_from_cfg(cfg)
+    gm = _gpu_map(cfg["map_origin"], cfg["resolution"], cfg["map_size"])
+    gm.upload_distance(om.distance())
+    origin, size = np.asarray(cfg["map_origin"], float), np.asarray(cfg["map_size"], float)
+    rng = fx.Rng(31)
+    pos = origin + 1e-3 + rng.uniform((4000, 3)) * (size - 2e-3)   # includes points in the border cells
+    boxes = np.concatenate([origin + rng.uniform((12, 3)) * size, rng.uniform((12, 3)) - 0.5, 0.2 + rng.uniform((12, 3))], axis=1)
+    d_ref, g_ref, c_ref = om.query_dynamic(pos, boxes, time)
+    d, g, c = gm.query_dynamic(pos, boxes, time)
+    assert np.array_equal(d, d_ref) and np.array_equal(g, g_ref) and np.array_equal(c, c_ref)
+    d0, g0, _ = gm.query_dynamic(pos, np.zeros((0, 9)), time)   # no boxes: min with 1e7 = static field
+    ds, _, _ = om.query_dynamic(pos, np.zeros((0, 9)), time)
+    assert np.array_equal(d0, ds)
