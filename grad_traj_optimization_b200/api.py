@@ -58,7 +58,7 @@ class SdfMap:
         self.origin, self.resolution, self.size, self.device = o.copy(), float(resolution), s.copy(), int(device)
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:  # (module globals are gone at interpreter shutdown)
             lib().gtop_sdf_destroy(self.h)
             self.h = None
 
@@ -204,7 +204,7 @@ class ProblemSet:
         return cls(h, p, int(device))
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().gtop_problems_destroy(self.h)
             self.h = None
 
