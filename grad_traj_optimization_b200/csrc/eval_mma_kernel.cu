@@ -45,7 +45,8 @@
 
 namespace gtop {
 
-// resident CTAs per SM asked of the compiler (register cap = 65536 / (32 * warps * MINB))
+// resident CTAs per SM asked of the compiler: 19 -> a cap of 96 registers, i.e. 5 warps per scheduler (the register
+// file is per scheduler: 16384 / (96 * 32) = 5.3), 20 per SM; 24 / 28 warps at 80 / 72 registers measured slower
 #ifndef GTOP_MMA_MINB
 #define GTOP_MMA_MINB 19
 #endif
