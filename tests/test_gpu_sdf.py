@@ -236,3 +236,23 @@ def test_dynamic_box_query_bit_exact(gtop_lib, time):
     d0, g0, _ = gm.query_dynamic(pos, np.zeros((0, 9)), time)   # no boxes: min with 1e7 = static field
     ds, _, _ = om.query_dynamic(pos, np.zeros((0, 9)), time)
     assert np.array_equal(d0, ds)
+
+
+@pytest.mark.parametrize("name", ["text_input", "opti_node"])
+def test_windowed_update_golden(gtop_lib, name):
+    """committed golden digest of a windowed rebuild on the upstream fixtures (tests/golden/make_golden.py)"""
+    import hashlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import window_case
+    cfg = fx.load_cfg(name)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "fixtures_edt.npz"))
+    gm = _gpu_map(cfg["map_origin"], cfg["resolution"], cfg["map_size"])
+    gm.update(cfg["obstacles"])
+    d0 = gm.distance()
+    lo, hi, extra = window_case(cfg)
+    gm.reset_range(lo, hi), gm.set_occupancy(extra), gm.set_update_range(lo, hi), gm.update_esdf()
+    d = gm.distance()
+    assert np.array_equal(np.frombuffer(hashlib.sha256(d.tobytes()).digest(), dtype=np.uint8), gold[name + "_window_sha256"])
+    assert int((d != d0).sum()) == int(gold[name + "_window_changed"])
