@@ -169,7 +169,8 @@ __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double p
 // guarantees that all 32 lanes reach this call together (then the branch is made warp-uniform with a
 // vote); otherwise every lane decides for itself.
 template <bool kWarpUniform>
-__device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, double& gx, double& gy, double& gz) {
+__device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, double& gx, double& gy, double& gz,
+                                           unsigned* oob = nullptr, bool counted = true) {
   double dx = c.dx, dy = c.dy;
   const bool any_special = kWarpUniform ? __any_sync(kFull, c.special) : c.special;
   if (__builtin_expect(any_special, 0)) {
@@ -190,6 +191,7 @@ __device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, doubl
   const double ex0 = fma(dy, e10 - e00, e00), ex1 = fma(dy, e11 - e01, e01);
   gx = fma(c.dz, ex1 - ex0, ex0);                         // :234-239
   if (__builtin_expect(any_special, 0)) {
+    if (oob) *oob += (!c.in_map && counted) ? 1u : 0u;     // out-of-map samples are counted on the rare path only
     dist = c.in_map ? dist : -1.0;                        // :187, H3
     gx = (c.in_map && !c.xlow) ? gx : 0.0;
     gy = (c.in_map && !c.ylow) ? gy : 0.0;

@@ -5,8 +5,10 @@
 // Replaces GradTrajOptimizer::getCostAndGradient (src/grad_traj_optimizer.cpp:281-448 of the
 // reference), same maths as eval_kernel.cu; what changes is the work decomposition:
 //
-//   warp = 8 trajectories x 4 lanes.  Lane (g, j) = (lane >> 2, lane & 3) evaluates sample 4*it + j of
-//   trajectory g in iteration `it` of the current segment (8 iterations at N_s = 30).
+//   warp = 8 trajectories x 4 lanes.  Segments are walked in pairs whose samples are numbered consecutively;
+//   lane (g, j) = (lane >> 2, lane & 3) evaluates slot 4*it + j of trajectory g in iteration `it` of the current
+//   pair (15 iterations per pair at N_s = 30: 75 per 10 segments where a per-segment loop needs 80, because 30
+//   samples leave two of the four lanes idle in every eighth iteration).
 //
 //   * The per-sample contribution to the gradient rows of the segment's two waypoints,
 //         G[a][r] += dt * (sA_a * phi_r(t) + sB_a * phi_r'(t)),   phi_r(t) = sum_i t^i Linv[i][r]
@@ -33,8 +35,12 @@
 //     latency hides behind the second half of the iteration.
 //   * The smoothness cost is accumulated from the gradient rows (d_u * (R d)_u) while they are formed;
 //     the rows of the fixed start / end state are added before / after the segment loop.
-//   * The boundary derivatives live in a four-waypoint ring per trajectory (shared memory independent of m),
-//     refilled from x by cp.async one segment ahead.
+//   * The boundary derivatives live in a six-waypoint ring per trajectory (shared memory independent of m),
+//     refilled from x by cp.async one pair of segments ahead.
+//   * The tables carry the pair schedule (which sample a slot holds, its quadrature weight, zero weights for idle
+//     slots): the loop only picks each lane's coefficient set and, once per pair, moves the first segment's
+//     waypoint rows out of the C fragments (in the one iteration that holds samples of both segments the DMMAs are
+//     issued twice, once per segment, against B fragments that are zero for the other segment's lanes).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -61,19 +67,20 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // per-warp shared memory, in doubles:
-//   ring [8][37]        boundary derivatives of FOUR consecutive waypoints per trajectory, [slot][axis][p,v,a] with
-//                       slot = waypoint % 4: segment s needs waypoints s, s+1 for its coefficients and s-1, s, s+1 for
-//                       the smoothness rows of waypoint s; waypoint s+2 is copied from x into the fourth slot with
-//                       cp.async WHILE segment s runs, so the read of x never stalls a warp.  Independent of m (a full
-//                       copy of x was 8 x 9(m+1) doubles: 6.3 KB per warp at m = 10, 18 KB at m = 30); stride 37 is
+//   ring [8][55]        boundary derivatives of SIX consecutive waypoints per trajectory, [slot][axis][p,v,a] with
+//                       slot = waypoint % 6: a pair of segments (s, s+1) needs waypoints s-1 .. s+2 (coefficients and
+//                       the smoothness rows of waypoints s, s+1), and waypoints s+3, s+4 are copied from x with
+//                       cp.async WHILE the pair runs, so the read of x never stalls a warp.  Independent of m (a full
+//                       copy of x was 8 x 9(m+1) doubles: 6.3 KB per warp at m = 10, 18 KB at m = 30); stride 55 is
 //                       odd -> the 8 trajectories of a warp sit in distinct banks
-//   coef [8][15][2]     coefficient pairs of the current segment, 15 16-byte elements per trajectory:
+//   coef [2][8][15][2]  coefficient pairs of the two segments of the current pair, 15 16-byte elements per trajectory:
 //                       per axis (c0,c1) (c2,c3) (c4,c5) (2c2,3c3) (4c4,5c5).  The 240-byte trajectory
 //                       stride puts the 8 trajectories of a warp in the 8 distinct 16-byte bank groups
 //                       both for the loads (fixed element) and the stores (element varies with the lane)
 //   scr  [8][9]         finished collision-gradient rows of one waypoint (3 axes x p,v,a)
-constexpr int kRing = 37;
-__host__ __device__ inline int mma_warp_smem_doubles() { return 8 * kRing + 240 + 72; }
+constexpr int kRingSlots = 6;
+constexpr int kRing = kRingSlots * 9 + 1;
+__host__ __device__ inline int mma_warp_smem_doubles() { return 8 * kRing + 2 * 240 + 72; }
 
 // coefficients c[a][i] = sum_r Linv[i][r] * dseg[a][r], summed in ascending dense-column order of L
 // (start derivatives first, except for the last segment whose end derivatives live in columns 3..5
@@ -140,7 +147,7 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   double* wbase = smem + warp * per_warp;
   double* ring = wbase + g * kRing;
   double2* coef = reinterpret_cast<double2*>(wbase + 8 * kRing) + g * 15;  // this trajectory's 15 pairs
-  double* scr = wbase + 8 * kRing + 240 + g * 9;
+  double* scr = wbase + 8 * kRing + 2 * 240 + g * 9;
 
   // all 8 trajectories of the group belong to one problem (host-checked: starts_per_problem % 8 == 0)
   const int64_t pid = (gb0 / starts_per_problem) % num_problems;
@@ -150,22 +157,23 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   // ---- 1. boundary derivatives of waypoints 0, 1 (and 2, in flight) into the ring ------------------------------
   // waypoint w: the fixed start / end state (Df) for w = 0 / m, the free derivatives x[a*P + 3(w-1) + q] otherwise;
   // copied global -> shared with cp.async (no register staging, no stall until the values are needed)
-  auto fetch_waypoint = [&](int w) {
-    double* dst = ring + (w & 3) * 9;
-    for (int i = j; i < 9; i += 4) {
-      const int a = i / 3, q = i - 3 * a;
-      const double* src = w == 0 ? pr + PL.off_Df + a * 6 + q : (w == m ? pr + PL.off_Df + a * 6 + 3 + q : x + a * P + 3 * (w - 1) + q);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + i)), "l"(src)
-                   : "memory");
+  auto fetch_waypoint = [&](int w) {  // (a waypoint past the end still commits its — empty — group)
+    if (w <= m) {
+      double* dst = ring + (w % kRingSlots) * 9;
+      for (int i = j; i < 9; i += 4) {
+        const int a = i / 3, q = i - 3 * a;
+        const double* src = w == 0 ? pr + PL.off_Df + a * 6 + q : (w == m ? pr + PL.off_Df + a * 6 + 3 + q : x + a * P + 3 * (w - 1) + q);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + i)), "l"(src)
+                     : "memory");
+      }
     }
-  };
-  auto fetch_wait = [&]() {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per waypoint, in waypoint order
   };
   fetch_waypoint(0);
   fetch_waypoint(1);
-  fetch_wait();
+  fetch_waypoint(2);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
 
   double Jc = 0.0, js = 0.0;
   // smoothness cost, rows of the fixed start waypoint (column band of R, :326-327): needs waypoints 0 and 1
@@ -185,36 +193,111 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   const double kA = -E.alpha * E.alpha_over_r * S.res_inv;  // gd*cd = -(alpha^2/r) e^2; grad scale 1/res
   double* __restrict__ gout = grad_out + b * n;
 
-  for (int s = 0; s < m; ++s) {
-    if (s >= 1) fetch_wait();  // waypoint s+1, requested during segment s-1, has landed
-    // waypoint s+2 replaces waypoint s-2 (last read by the combine step of segment s-1) while this segment runs
-    if (s + 2 <= m) fetch_waypoint(s + 2);
-    const double* wpm = ring + ((s + 3) & 3) * 9;  // waypoint s-1 (s >= 1)
-    const double* wp0 = ring + (s & 3) * 9;        // waypoint s
-    const double* wp1 = ring + ((s + 1) & 3) * 9;  // waypoint s+1
+  // rows of waypoint w (the start derivatives of segment w, which also collected the end derivatives of segment
+  // w-1 in place) are complete: out of the C fragments, then smoothness rows and output
+  auto flush_rows = [&](int w) {  // collision rows of waypoint w out of the C fragments
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int r = deriv_of_col(2 * j + e, w);
+      if (r >= 0 && r < 3) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          scr[a * 3 + r] = G[a][e];  // w = 0: the fixed start state, never read
+          G[a][e] = 0.0;
+        }
+      }
+    }
+    __syncwarp();
+  };
+  auto combine_rows = [&](int w) {
+    if (w >= 1) {
+      const double* wpm = ring + ((w - 1) % kRingSlots) * 9;  // waypoint w-1
+      const double* wp0 = ring + (w % kRingSlots) * 9;        // waypoint w
+      const double* wp1 = ring + ((w + 1) % kRingSlots) * 9;  // waypoint w+1
+      // smoothness rows 2 Rfp' df + 2 Rpp dp (:330-332) from the band of R, combined with the collision
+      // rows and written out (:425-431).  The same row products give the interior rows of the smoothness
+      // cost d' R d (:326-327).  Lane r = j < 3 takes derivative r of the three axes: one band row per lane,
+      // the window of the ring read as shared-memory broadcasts.
+      if (j < 3) {
+        const int r = j, jj = 3 * (w - 1) + r;
+        const double* __restrict__ band = pr + PL.off_Rg + jj * 9;
+        double bnd[9];
+#pragma unroll
+        for (int u = 0; u < 9; ++u) bnd[u] = __ldg(band + u);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          double gs = 0.0;  // window = waypoints w-1, w, w+1 of axis a
+#pragma unroll
+          for (int u = 0; u < 3; ++u) gs = fma(wpm[a * 3 + u], bnd[u], gs);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) gs = fma(wp0[a * 3 + u], bnd[3 + u], gs);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) gs = fma(wp1[a * 3 + u], bnd[6 + u], gs);
+          js = fma(gs, wp0[a * 3 + r], js);
+          const double val = (E.ws * (2.0 * gs) + E.wc * scr[a * 3 + r]) + 1e-5;
+          if (live) gout[a * P + jj] = val;
+        }
+      }
+      __syncwarp();
+    }
+  };
+
+  // Segments are walked in pairs (sa, sb) = (2p, 2p+1): the ns_a + ns_b samples of a pair are numbered consecutively
+  // and iteration `it` evaluates slots 4 it + j, so a sample count that is not a multiple of 4 (30 upstream) idles
+  // lanes once per pair instead of once per segment (75 instead of 80 iterations per 10 segments).  The tables carry
+  // the schedule (which sample a slot holds, its quadrature weight, zero weights for idle slots); the loop only has to
+  // pick each lane's coefficient set and to move the first segment's waypoint rows out of the C fragments when its
+  // last sample has gone in.
+  double2* coefB = coef + 8 * 15;  // coefficients of the pair's second segment (same layout, next 240 doubles)
+  for (int sa = 0; sa < m; sa += 2) {
+    const int sb = sa + 1;
+    const bool hasb = sb < m;
+    // waypoints sa+3, sa+4 (for the next pair) start flying; everything older — sa .. sa+2 — has landed
+    fetch_waypoint(sa + 3);
+    fetch_waypoint(sa + 4);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    bool flushed = false;
     if (!E.skip_collision) {
-      const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + s * 36);
-      if (s == m - 1) coef_phase<true>(wp0, wp1, LiTP, coef, j);
-      else coef_phase<false>(wp0, wp1, LiTP, coef, j);
+      {
+        const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + sa * 36);
+        const double* wp0 = ring + (sa % kRingSlots) * 9;
+        const double* wp1 = ring + ((sa + 1) % kRingSlots) * 9;
+        if (sa == m - 1) coef_phase<true>(wp0, wp1, LiTP, coef, j);
+        else coef_phase<false>(wp0, wp1, LiTP, coef, j);
+      }
+      if (hasb) {
+        const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + sb * 36);
+        const double* wp0 = ring + (sb % kRingSlots) * 9;
+        const double* wp1 = ring + ((sb + 1) % kRingSlots) * 9;
+        if (sb == m - 1) coef_phase<true>(wp0, wp1, LiTP, coefB, j);
+        else coef_phase<false>(wp0, wp1, LiTP, coefB, j);
+      }
       __syncwarp();
 
-      const int ns = (int)pr[PL.off_ns + s];
-      const int nit = (ns + 3) >> 2;
-      // this lane's 64-byte table record of the current iteration; advanced by 4 slots per iteration
-      const double2* __restrict__ tq = reinterpret_cast<const double2*>(pr + PL.off_TQ) + (size_t)s * (PL.nsp >> 2) * 12 + j;
-      const double2* __restrict__ pl = reinterpret_cast<const double2*>(pr + PL.off_PL) + (size_t)s * (PL.nsp >> 2) * 32 + lane;
-      // lane-ordered tables (gtop_types.cuh): the 4 sample slots of an iteration read 64 contiguous bytes per
-      // load of the time record (1 L1 wavefront), the 32 lanes 512 contiguous bytes of B fragments (4 wavefronts)
-      double2 ta, tb, tc;  // (1,t) (t2,t3) (t4,t5) of the current sample, requested one iteration ahead
+      const int nsa = (int)pr[PL.off_ns + sa], nsb = hasb ? (int)pr[PL.off_ns + sb] : 0;
+      const int nit = (nsa + nsb + 3) >> 2;
+      const bool mixed = nsb > 0 && (nsa & 3) != 0;  // one iteration holds samples of both segments
+      // this lane samples the second segment from iteration ubl on (the mixed iteration splits the lanes)
+      const int ubl = nsb > 0 ? (nsa >> 2) + ((mixed && j < (nsa & 3)) ? 1 : 0) : 0x7fffffff;
+      // the first segment's last sample goes in at iteration uf (its rows are flushed after that iteration's DMMAs)
+      const int uf = nsb > 0 ? (mixed ? (nsa >> 2) : (nsa >> 2) - 1) : -1;
+      if (nsb > 0 && uf < 0) flush_rows(sa), flushed = true;  // (degenerate: the first segment has no samples)
+      // lane-ordered tables of the pair (gtop_types.cuh): the 4 sample slots of an iteration read 64 contiguous bytes
+      // per load of the time record (1 L1 wavefront), the 32 lanes 512 contiguous bytes of B fragments (4 wavefronts)
+      const double2* __restrict__ tq = reinterpret_cast<const double2*>(pr + PL.off_TQ) + (size_t)(sa >> 1) * PL.nit2 * 12 + j;
+      const double2* __restrict__ pl = reinterpret_cast<const double2*>(pr + PL.off_PL) + (size_t)(sa >> 1) * (PL.nit2 + 1) * 32 + lane;
+      double2 ta, tb, tc;  // (dt,t) (t2,t3) (t4,t5) of the current sample, requested one iteration ahead
       if (nit > 0) ta = ldg_tab(tq), tb = ldg_tab(tq + 4), tc = ldg_tab(tq + 8);
-      double jseg = 0.0;
+      const double2* cf = 0 >= ubl ? coefB : coef;  // this lane's coefficient set in the current iteration
       for (int it = 0; it < nit; ++it, tq += 12, pl += 32) {
         const double t = ta.y, t2 = tb.x, t3 = tb.y, t4 = tc.x, t5 = tc.y;
+        const double wdt = ta.x;  // dt of the slot's segment; 0 for idle slots, which evaluate a segment start in vain
         double pos[3], vel[3], c1[3];
         float pf[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          const double2 c01 = coef[a * 5 + 0], c23 = coef[a * 5 + 1], c45 = coef[a * 5 + 2];
+          const double2 c01 = cf[a * 5 + 0], c23 = cf[a * 5 + 1], c45 = cf[a * 5 + 2];
           c1[a] = c01.y;
           // getPositionFromCoeff (:457-465): left-to-right, unfused, then float
           double pa = __dadd_rn(c01.x, __dmul_rn(c01.y, t));
@@ -229,7 +312,7 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
         sdf_gather<kNoAlloc>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          const double2 e01 = coef[a * 5 + 3], e23 = coef[a * 5 + 4];
+          const double2 e01 = cf[a * 5 + 3], e23 = cf[a * 5 + 4];
           // getVelocityFromCoeff (:477-485)
           double va = __dadd_rn(c1[a], __dmul_rn(e01.x, t));
           va = __dadd_rn(va, __dmul_rn(e01.y, t2));
@@ -239,104 +322,54 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
         }
         // B fragments of this sample (column g of the lane), then the time record of the next sample
         const double2 bAB = ldg_tab(pl);
-        const double bA = bAB.x, bB = bAB.y;
         if (it + 1 < nit) ta = ldg_tab(tq + 12), tb = ldg_tab(tq + 16), tc = ldg_tab(tq + 20);
 
-#ifdef GTOP_EXP_EXTRA_LDS  // sensitivity experiment: +10 coefficient loads (20 L1 wavefronts) per iteration
-        {
-          double sx = 0.0, sy = 0.0;
-#pragma unroll
-          for (int q = 0; q < 10; ++q) {
-            double vx, vy;
-            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(vx), "=d"(vy) : "r"((unsigned)__cvta_generic_to_shared(&coef[q])));
-            sx += vx, sy = vy;
-          }
-          if (sx == 1.2345e300) jseg += sy;
-        }
-#endif
-#ifdef GTOP_EXP_EXTRA_DP  // sensitivity experiment: +20 independent DFMAs per iteration
-        {
-          double e0 = vel[0], e1 = vel[1], e2 = vel[2], e3 = c1[0];
-#pragma unroll
-          for (int q = 0; q < 5; ++q)
-            e0 = fma(e0, 1.0000001, 1e-9), e1 = fma(e1, 1.0000001, 1e-9), e2 = fma(e2, 1.0000001, 1e-9), e3 = fma(e3, 1.0000001, 1e-9);
-          if (e0 + e1 + e2 + e3 == 1.2345e300) jseg += e0;
-        }
-#endif
-#ifdef GTOP_EXP_EXTRA_INT  // sensitivity experiment: a chain of 40 dependent integer instructions per iteration
-        {
-          int k0 = it, k1 = lane;
-#pragma unroll
-          for (int q = 0; q < 20; ++q) k0 = k0 * 3 + k1, k1 = k1 * 5 + k0;
-          if (k0 + k1 == 0x7fffffff) jseg += 1.0;
-        }
-#endif
         const double vn2 = fma(vel[2], vel[2], fma(vel[1], vel[1], fma(vel[0], vel[0], 1e-300)));
         const double vnorm = sqrt_pos(vn2) + 1e-5;  // :358 (the 1e-300 keeps v = 0 finite; absorbed by 1e-5)
         const double inv_vn = rcp_pos(vnorm);
 
         double dist, gd[3];
-        sdf_finish<true>(cell, dist, gd[0], gd[1], gd[2]);  // the sample loop is warp-uniform
-        const bool real = 4 * it + j < ns;  // padding slots evaluate the segment start with zero weights
-        oob += (!cell.in_map && real) ? 1u : 0u;
+        // (the sample loop is warp-uniform; out-of-map samples of real — non-idle — slots are counted)
+        sdf_finish<true>(cell, dist, gd[0], gd[1], gd[2], &oob, __double2hiint(wdt) != 0);
 
         // exp(-(d-d0)/r) (:509/:514) = 2^((d0-d)*log2(e)/r)
         const double ee = exp2_tab(fma(dist, E.neg_log2e_over_r, E.d0_log2e_over_r), xtab);
         const double ev = ee * vnorm;
-        jseg += real ? ev : 0.0;           // cost: cd*|v| = alpha*ee*vnorm (alpha, dt applied later)
+        Jc = fma(ev, wdt, Jc);  // cost: cd*|v|*dt = alpha*ee*vnorm*dt (:374; alpha applied at the end)
         // sA_a = gd*grad_a*cd*|v| = kA * ee^2 * vnorm * g_a      (:378, extra cd reproduced — H4)
         // sB_a = cd*v_a/|v|       = alpha * ee * v_a / vnorm     (:379)
         const double sAc = kA * (ee * ev);
         const double sBc = E.alpha * (ee * inv_vn);
+        double fa[3], fb[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) fa[a] = sAc * gd[a], fb[a] = sBc * vel[a];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          dmma884(G[a][0], G[a][1], sAc * gd[a], bA);   // += sA_a(sample) * dt phi_r(sample), straight into G
-          dmma884(G[a][0], G[a][1], sBc * vel[a], bB);
+          dmma884(G[a][0], G[a][1], fa[a], bAB.x);   // += sA_a(sample) * dt phi_r(sample), straight into G
+          dmma884(G[a][0], G[a][1], fb[a], bAB.y);
+        }
+        cf = it + 1 >= ubl ? coefB : coef;
+        if (__builtin_expect(it == uf, 0)) {
+          // the first segment is complete: its waypoint rows leave the C fragments (they are combined with the
+          // smoothness rows after the loop).  In a mixed iteration record `it` carried the first segment's lanes only;
+          // the second segment's lanes go in now through the pair's extra record
+          flush_rows(sa), flushed = true;
+          if (mixed) {
+            const double2 bX = ldg_tab(pl + (size_t)(PL.nit2 - it) * 32);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              dmma884(G[a][0], G[a][1], fa[a], bX.x);
+              dmma884(G[a][0], G[a][1], fb[a], bX.y);
+            }
+          }
         }
       }
-      Jc = fma(jseg, pr[PL.off_dt + s], Jc);
-
     }
-
-    // ---- the rows of waypoint s (start derivatives of segment s) are complete -----------------------
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int r = deriv_of_col(2 * j + e, s);
-      if (r >= 0 && r < 3) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          scr[a * 3 + r] = G[a][e];  // s = 0: the fixed start state, never read
-          G[a][e] = 0.0;
-        }
-      }
-    }
-    __syncwarp();
-    if (s >= 1) {
-      // smoothness rows 2 Rfp' df + 2 Rpp dp (:330-332) from the band of R, combined with the collision
-      // rows and written out (:425-431).  The same row products give the interior rows of the smoothness
-      // cost d' R d (:326-327).  Lane r = j < 3 takes derivative r of the three axes: one band row per lane,
-      // the window of the ring read as shared-memory broadcasts.
-      if (j < 3) {
-        const int r = j, jj = 3 * (s - 1) + r;
-        const double* __restrict__ band = pr + PL.off_Rg + jj * 9;
-        double bnd[9];
-#pragma unroll
-        for (int u = 0; u < 9; ++u) bnd[u] = __ldg(band + u);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          double gs = 0.0;  // window = waypoints s-1, s, s+1 of axis a
-#pragma unroll
-          for (int u = 0; u < 3; ++u) gs = fma(wpm[a * 3 + u], bnd[u], gs);
-#pragma unroll
-          for (int u = 0; u < 3; ++u) gs = fma(wp0[a * 3 + u], bnd[3 + u], gs);
-#pragma unroll
-          for (int u = 0; u < 3; ++u) gs = fma(wp1[a * 3 + u], bnd[6 + u], gs);
-          js = fma(gs, wp0[a * 3 + r], js);
-          const double val = (E.ws * (2.0 * gs) + E.wc * scr[a * 3 + r]) + 1e-5;
-          if (live) gout[a * P + jj] = val;
-        }
-      }
-      __syncwarp();
+    if (!flushed) flush_rows(sa);
+    combine_rows(sa);
+    if (hasb) {
+      flush_rows(sb);
+      combine_rows(sb);
     }
   }
   if (oob_counter != nullptr) {
@@ -348,8 +381,8 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
   // the ring still holds after the last segment
   if (j < 3) {
     const double* __restrict__ band = pr + PL.off_Rc + (3 * m + j) * 9;  // band entries 0..5 <-> waypoints m-1, m
-    const double* wa = ring + ((m - 1) & 3) * 9;
-    const double* wb = ring + (m & 3) * 9;
+    const double* wa = ring + ((m - 1) % kRingSlots) * 9;
+    const double* wb = ring + (m % kRingSlots) * 9;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       double y = 0.0;

@@ -60,18 +60,25 @@ inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 
 //   Df    [3][6]         fixed derivatives per axis: p0,v0,a0,pEnd,vEnd,aEnd
 //   LinvT [m][6][6]      transpose of Linv (col = power): the coefficient step reads 6 contiguous
 //                        doubles per derivative instead of a stride-6 column
-// Sections read by the multi-start kernel k_eval_mma (eval_mma_kernel.cu); nsp = ns_cap rounded up to 4:
-//   TQ    [m][nsp/4][3][4][2]  powers of the sample times in the order the lanes read them: iteration `it` of the
-//                        kernel evaluates samples 4 it + j (j = lane & 3); part 0/1/2 of slot j = (1,t) (t^2,t^3)
-//                        (t^4,t^5), the four slots of a part contiguous (one 64-byte L1 wavefront per 128-bit
-//                        load).  Padding slots (k >= ns) are all zero: they evaluate the segment's start point.
-//   PL    [m][nsp/4][32][2]    B fragments of the gradient DMMAs, one 16-byte pair per lane = 4 g + j of iteration it:
-//                        (dt_s * phi_r(t_k), dt_s * phi_r'(t_k)), k = 4 it + j, phi_r(t) = sum_i t^i Linv_s[i][r] the
-//                        basis function of local derivative r = deriv_of_col(g, s) (T Ldp and T V Ldp of :376-381,
-//                        which depend on the problem only).  Column g <-> derivative r alternates with the
-//                        segment parity so that the end-derivative columns of segment s are the
-//                        start-derivative columns of s+1.  Padding slots and columns 6, 7 are zero: they
-//                        contribute nothing.
+// Sections read by the multi-start kernel k_eval_mma (eval_mma_kernel.cu).  The kernel walks the segments in PAIRS
+// (2p, 2p+1): the ns_a + ns_b samples of a pair are numbered consecutively (slot q < ns_a: sample q of the first
+// segment, else sample q - ns_a of the second) and iteration u of the pair evaluates slots 4u + j (j = lane & 3), so
+// that a sample count that is not a multiple of 4 (30 in the reference) leaves idle slots once per pair, not once
+// per segment.  npair = ceil(m/2), nit2 = ceil(2 ns_cap / 4) iterations per pair:
+//   TQ    [npair][nit2][3][4][2]   powers of the sample times in the order the lanes read them: part 0/1/2 of slot j =
+//                        (dt_s,t) (t^2,t^3) (t^4,t^5) — the quadrature weight dt_s of the slot's segment sits where t^0
+//                        would —, the four slots of a part contiguous (one 64-byte L1 wavefront per
+//                        128-bit load).  Idle slots are all zero: they evaluate a segment's start point.
+//   PL    [npair][nit2+1][32][2]   B fragments of the gradient DMMAs, one 16-byte pair per lane = 4 g + j of iteration u:
+//                        (dt_s * phi_r(t_k), dt_s * phi_r'(t_k)) of the slot's segment s and sample k, phi_r(t) =
+//                        sum_i t^i Linv_s[i][r] the basis function of local derivative r = deriv_of_col(g, s) (T Ldp
+//                        and T V Ldp of :376-381, which depend on the problem only).  Column g <-> derivative r
+//                        alternates with the segment parity so that the end-derivative columns of segment s are the
+//                        start-derivative columns of s+1.  Idle slots and columns 6, 7 are zero: they contribute
+//                        nothing.  In the one iteration that mixes both segments of a pair (u = ns_a / 4 when ns_a is
+//                        not a multiple of 4) record u carries the first segment's lanes only and record nit2 (the
+//                        extra one) the second segment's: the kernel issues the DMMAs once per record and closes the
+//                        first segment's waypoint rows in between.
 //   LiTP  [m][3][6][2]   (Linv[2p][r], Linv[2p+1][r]): coefficient step, two powers per 128-bit load
 //   T     [m]            segment times T_s (segment_time, grad_traj_optimizer.cpp:73-81): post-hoc metrics kernel
 struct ProbLayout {
@@ -80,6 +87,8 @@ struct ProbLayout {
   int n;       // NLopt variables = 3P
   int ns_cap;  // samples_per_segment (table capacity)
   int nsp;     // ns_cap rounded up to a multiple of 4
+  int npair;   // segment pairs = ceil(m/2)
+  int nit2;    // iterations of k_eval_mma per pair at full sample count = ceil(2 ns_cap / 4)
   int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df, off_LinvT;
   int off_LiTP, off_TQ, off_PL, off_T;
   int stride;
@@ -109,8 +118,10 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   o = (o + 7) & ~7;  // 64-byte aligned slots (relative to the 16-byte aligned record)
   L.off_LiTP = o, o += m * 36;
   o = (o + 7) & ~7;
-  L.off_TQ = o, o += m * (L.nsp / 4) * 24;
-  L.off_PL = o, o += m * (L.nsp / 4) * 64;
+  L.npair = (m + 1) / 2;
+  L.nit2 = (2 * ns_cap + 3) / 4;
+  L.off_TQ = o, o += L.npair * L.nit2 * 24;
+  L.off_PL = o, o += L.npair * (L.nit2 + 1) * 64;
   L.off_T = o, o += m;
   L.stride = (o + 7) & ~7;  // keep every record 64-byte aligned
   return L;

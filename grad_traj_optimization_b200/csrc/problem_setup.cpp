@@ -183,19 +183,22 @@ void pack_record(const ProblemHost& p, double* rec) {
     for (int i = 0; i < 6; ++i)
       for (int r = 0; r < 6; ++r) rec[L.off_LinvT + s * 36 + r * 6 + i] = p.Linv[(size_t)s * 36 + i * 6 + r];
   // ---- tables of the multi-start (DMMA) kernel ------------------------------------------------
-  const int NS = p.ns_cap, NSP = L.nsp;
+  const int NS = p.ns_cap;
   for (int s = 0; s < p.m; ++s) {
     const double* tt = &p.tt[(size_t)s * 5 * NS];
     const int ns = (int)p.ns[s];
-    // TQ / PL (gtop_types.cuh): sample slot k = 4 it + j; padding slots stay zero (memset above)
-    for (int k = 0; k < NSP && k < ns; ++k) {
-      const int it = k >> 2, j = k & 3;
+    const int ns_first = (s & 1) ? (int)p.ns[s - 1] : ns;
+    // TQ / PL in the pair schedule (gtop_types.cuh); idle slots stay zero (memset above)
+    for (int k = 0; k < ns; ++k) {
+      int u, j, rec_pl;
+      setup_pair_slot(s, k, ns_first, L.nit2, &u, &j, &rec_pl);
       double pw[6] = {1.0, 0, 0, 0, 0, 0};  // tau_i = t^i (:549)
       for (int q = 1; q <= 5; ++q) pw[q] = tt[(size_t)(q - 1) * NS + k];
-      double* tq = rec + L.off_TQ + ((size_t)s * (NSP / 4) + it) * 24;
+      double* tq = rec + L.off_TQ + ((size_t)(s >> 1) * L.nit2 + u) * 24;
       for (int part = 0; part < 3; ++part) tq[(part * 4 + j) * 2] = pw[2 * part], tq[(part * 4 + j) * 2 + 1] = pw[2 * part + 1];
+      tq[j * 2] = p.dt[s];  // t^0 is not read: its place carries the slot's quadrature weight dt_s (0 for idle slots)
       // (dt * phi_r(t_k), dt * phi_r'(t_k)), phi_r(t) = sum_i t^i Linv[i][r]: T Ldp and T V Ldp of :376-381 times dt (:381)
-      double* pl = rec + L.off_PL + ((size_t)s * (NSP / 4) + it) * 64;
+      double* pl = rec + L.off_PL + ((size_t)(s >> 1) * (L.nit2 + 1) + rec_pl) * 64;
       for (int g = 0; g < 8; ++g) {
         const int r = deriv_of_col(g, s);
         if (r < 0) continue;

@@ -165,6 +165,17 @@ GTOP_HD inline void setup_x0_box(const double* pos, const double* vel, const dou
   *ub = (q == 0 ? c : 0.0) + half;
 }
 
+// Pair schedule of k_eval_mma (gtop_types.cuh): where sample k of segment s sits.  ns_first = sample count of the
+// pair's first segment.  Returns the TQ / PL iteration u and slot j; *pl_record = the PL record (u, or nit2 for the
+// second segment's lanes in the iteration that mixes both segments).
+GTOP_HD inline void setup_pair_slot(int s, int k, int ns_first, int nit2, int* u, int* j, int* pl_record) {
+  const int second = s & 1;
+  const int q = second ? ns_first + k : k;
+  *u = q >> 2, *j = q & 3;
+  const bool mixed_iter = (ns_first & 3) != 0 && *u == (ns_first >> 2);
+  *pl_record = (second && mixed_iter) ? nit2 : *u;
+}
+
 // B fragments of the gradient DMMAs for one sample and one local derivative r (gtop_types.cuh, PL):
 // (dt * phi_r(t), dt * phi_r'(t)), phi_r(t) = sum_i t^i Linv[i][r]; pw[i] = t^i
 GTOP_HD inline void setup_basis_pair(const double pw[6], const double* Li /* 36 */, int r, double dt, double* a_out,

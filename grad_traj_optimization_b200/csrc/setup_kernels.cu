@@ -40,7 +40,7 @@ __host__ __device__ inline size_t setup_smem_doubles(int m) { return (size_t)m *
 __global__ void __launch_bounds__(128) k_setup_problems(SetupArgs A) {
   extern __shared__ __align__(16) double sm[];
   const ProbLayout& L = A.PL;
-  const int m = L.m, NS = L.ns_cap, NSP = L.nsp, nd = 3 * m + 3, P = L.P;
+  const int m = L.m, NS = L.ns_cap, nd = 3 * m + 3, P = L.P;
   double* Mseg = sm;
   double* Linv = Mseg + (size_t)m * 36;
   double* dts = Linv + (size_t)m * 36;
@@ -100,10 +100,12 @@ __global__ void __launch_bounds__(128) k_setup_problems(SetupArgs A) {
     double pw[6];
     pw[0] = 1.0, pw[1] = tt[k];
     for (int q = 2; q <= 5; ++q) pw[q] = setup_pow(pw[1], q), tt[(size_t)(q - 1) * NS + k] = pw[q];  // :457-485, :549
-    const int it = k >> 2, j = k & 3;
-    double* tq = rec + L.off_TQ + ((size_t)s * (NSP / 4) + it) * 24;
+    int u, j, rec_pl;
+    setup_pair_slot(s, k, (s & 1) ? (int)nss[s - 1] : (int)nss[s], L.nit2, &u, &j, &rec_pl);
+    double* tq = rec + L.off_TQ + ((size_t)(s >> 1) * L.nit2 + u) * 24;
     for (int part = 0; part < 3; ++part) tq[(part * 4 + j) * 2] = pw[2 * part], tq[(part * 4 + j) * 2 + 1] = pw[2 * part + 1];
-    double* pl = rec + L.off_PL + ((size_t)s * (NSP / 4) + it) * 64;
+    tq[j * 2] = dts[s];  // the slot's quadrature weight in the place of t^0
+    double* pl = rec + L.off_PL + ((size_t)(s >> 1) * (L.nit2 + 1) + rec_pl) * 64;
     for (int g = 0; g < 8; ++g) {
       const int r = deriv_of_col(g, s);
       if (r < 0) continue;
