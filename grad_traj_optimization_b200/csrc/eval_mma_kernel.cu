@@ -51,10 +51,12 @@
 
 namespace gtop {
 
-// resident CTAs per SM asked of the compiler: 19 -> a cap of 96 registers, i.e. 5 warps per scheduler (the register
-// file is per scheduler: 16384 / (96 * 32) = 5.3), 20 per SM; 24 / 28 warps at 80 / 72 registers measured slower
+// resident CTAs per SM asked of the compiler: the kernel runs 20 warps per SM (96 registers: the register file is
+// per scheduler, 16384 / (96 * 32) = 5.3 -> 5 warps each); 17..20 all compile to 96 registers, with different
+// schedules — 18 measured fastest (0.3425 ms against 0.3456 at 19 / 20, 0.3451 at 17); 16 -> 126 registers, no
+// spills, 16 warps: 0.350; 24 -> 80 registers, 24 warps, 98 B of spills: 0.382
 #ifndef GTOP_MMA_MINB
-#define GTOP_MMA_MINB 19
+#define GTOP_MMA_MINB 18
 #endif
 // one warp per CTA: the kernel has no block-level cooperation, and small CTAs pack SMs evenly
 #ifndef GTOP_MMA_WARPS
