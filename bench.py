@@ -270,12 +270,12 @@ def run_ours(args):
         achieved = B * bytes_eval / (ms_step * 1e-3) / 1e9  # per-GPU kernel: one launch = B evaluations
         cpu = cpu_baseline(args, X[:min(B, 4096)], starts) if not args.no_cpu_baseline else None
         if fp64 and "dfma_peak_tflops" in fp64:
-            # executed FP64 work of k_eval_mma per trajectory-segment (ncu, profiles/r1_k_eval_mma_ncu.txt): 106.2
-            # DADD/DMUL + 33.5 DFMA warp instructions (32 lanes) + 6.0 DMMA (512 flops each)
-            flops_unit = (56.5 + 49.7) * 32 + 33.5 * 64 + 6.0 * 512
+            # executed FP64 work of k_eval_mma per trajectory-segment (ncu, profiles/r1_k_eval_mma_ncu.txt): 99.2
+            # DADD/DMUL + 32.5 DFMA warp instructions (32 lanes) + 6.0 DMMA (512 flops each)
+            flops_unit = (52.3 + 46.9) * 32 + 32.5 * 64 + 6.0 * 512
             tf = flops_unit * M_SEG * B / (ms_step * 1e-3) / 1e12
             fp64.update({"kernel_executed_tflops": tf, "frac_of_dfma_peak": tf / fp64["dfma_peak_tflops"],
-                         "fp64_unit_busy_ncu": "vector 45.5 % + DMMA 15.6 % of cycles (profiles/r1_k_eval_mma_ncu.txt)"})
+                         "fp64_unit_busy_ncu": "vector 44.5 % + DMMA 16.2 % of cycles (profiles/r1_k_eval_mma_ncu.txt)"})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
