@@ -197,6 +197,11 @@ int main(int argc, char** argv) {
     std::printf("%s; first segment x-coefficients:", solved ? "done" : "done (no solve)");
     for (int k = 0; k < 6; ++k) std::printf(" %.9g", coeff[k]);
     std::printf("\n");
+    // the evaluation opti_node runs on the result (src/opti_node.cpp:136-142, PolynomialTraj)
+    double met[GTOP_NUM_TRAJ_METRICS];
+    if (gtop_traj_metrics_host(opt.problems(), opt.derivatives().data(), 1, 0, 1, met) == GTOP_OK)
+      std::printf("trajectory: time %.6f s, length %.6f m, jerk %.6g, mean/max vel %.6g / %.6g, mean/max acc %.6g / %.6g\n", met[0],
+                  met[1], met[2], met[3], met[4], met[5], met[6]);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -105,6 +105,12 @@ def test_cpp_harness_end_to_end(gtop_lib, name, solver, tmp_path):
     T = gold_eval[name + "_seg_time"]
     dev = np.linalg.norm(sample_traj(gold[name + "_coeff_maxeval100"], T) - sample_traj(coeff, T), axis=1).max()
     assert dev <= 1e-4, "trajectory deviation %.3e m" % dev
+    # the evaluation opti_node runs on the result (opti_node.cpp:136-142): metrics of the dumped coefficients
+    from oracle import traj_metrics
+    ln = [x for x in r.stdout.splitlines() if x.startswith("trajectory:")][0]
+    vals = [float(v) for v in ln.replace(",", " ").replace("/", " ").split() if v.replace(".", "").replace("e", "").replace("-", "").replace("+", "").isdigit()]
+    ref = traj_metrics(coeff, T)
+    assert abs(vals[0] - ref[0]) <= 1e-5 and abs(vals[1] - ref[1]) <= 1e-4 * ref[1] and abs(vals[2] - ref[2]) <= 1e-4 * abs(ref[2])
 
 
 @pytest.mark.parametrize("name,starts", [("opti_node", 16), ("text_input", 8), ("opti_node", 5)])
