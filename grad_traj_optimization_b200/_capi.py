@@ -18,7 +18,7 @@ SYMBOLS = (
     "gtop_sdf_download_distance", "gtop_sdf_upload_distance", "gtop_sdf_download_occupancy",
     "gtop_sdf_upload_occupancy", "gtop_sdf_distance_device_ptr", "gtop_sdf_query", "gtop_sdf_query_dynamic", "gtop_problems_create_dense",
     "gtop_problems_create_from_paths", "gtop_problems_create_from_kino", "gtop_problems_create_from_paths_device",
-    "gtop_problems_create_from_kino_device", "gtop_problems_record", "gtop_traj_metrics_device", "gtop_traj_metrics_host", "gtop_problems_destroy", "gtop_problems_dims", "gtop_problems_set_params",
+    "gtop_problems_create_from_kino_device", "gtop_problems_record", "gtop_debug_pack_record", "gtop_traj_metrics_device", "gtop_traj_metrics_host", "gtop_problems_destroy", "gtop_problems_dims", "gtop_problems_set_params",
     "gtop_problems_seg_time", "gtop_problems_x0", "gtop_problems_bounds", "gtop_problems_dense_L",
     "gtop_problems_dense_R", "gtop_problems_Df", "gtop_eval_batch_device", "gtop_eval_batch_host",
     "gtop_problems_take_out_of_map", "gtop_kernel_launch_count", "gtop_coeff_from_x", "gtop_objective_ctx_create",
@@ -82,6 +82,7 @@ def lib():
         "gtop_problems_create_dense": (C.c_int, [i32, i32, dp, dp, dp, dp, pp, C.c_int, pvp]),
         "gtop_problems_create_from_paths": (C.c_int, [i32, i32, dp, pp, C.c_int, pvp]),
         "gtop_problems_record": (C.c_int, [vp, i32, dp, i64, C.POINTER(i64)]),
+        "gtop_debug_pack_record": (C.c_int, [i32, dp, pp, dp, i64, C.POINTER(i32)]),
         "gtop_traj_metrics_device": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
         "gtop_traj_metrics_host": (C.c_int, [vp, dp, i64, i64, i64, dp]),
         "gtop_problems_create_from_kino": (C.c_int, [i32, i32, dp, dp, dp, dp, pp, C.c_int, pvp]),

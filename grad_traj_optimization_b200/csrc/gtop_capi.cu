@@ -818,6 +818,24 @@ int gtop_problems_Df(const gtop_problems* p, int32_t i, double* Df) {
   return GTOP_OK;
 }
 
+// host-only: the packed record of one problem set up from a path, and the offsets of its sections (no device involved)
+int gtop_debug_pack_record(int32_t m, const double* waypoints, const gtop_params* prm, double* rec, int64_t cap,
+                           int32_t layout[16]) {
+  REQUIRE(m >= 2 && waypoints && layout, "bad argument");
+  if (int rc = check_params(prm)) return rc;
+  const ProbLayout L = make_layout(m, prm->samples_per_segment);
+  const int32_t lay[16] = {L.m,      L.ns_cap,  L.nsp,   L.npair,  L.nit2,   L.stride, L.off_dt, L.off_ns,
+                           L.off_tt, L.off_TQ,  L.off_PL, L.off_LiTP, L.off_Linv, L.off_T, L.off_Rc, L.off_Rg};
+  std::memcpy(layout, lay, sizeof(lay));
+  if (!rec) return GTOP_OK;
+  REQUIRE(cap >= L.stride, "record buffer too small");
+  ProblemHost h;
+  const std::string err = setup_from_path(m, waypoints, *prm, h);
+  if (!err.empty()) return fail(GTOP_E_INVALID, err);
+  pack_record(h, rec);
+  return GTOP_OK;
+}
+
 int gtop_problems_record(const gtop_problems* p, int32_t i, double* rec, int64_t cap, int64_t* len) {
   REQUIRE(p && i >= 0 && i < p->np, "bad argument");
   const int64_t n = p->layout.stride;

@@ -219,6 +219,11 @@ int gtop_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops)
 /* Self-check of the EDT's fast integer square root: the number of integers v in [1, vmax] for which it differs from
  * the IEEE sqrt((double)v) that SDFMap::updateESDF3d applies (sdf_map.cpp:356-360).  Must be 0 for vmax = 3*8192^2. */
 int gtop_debug_check_sqrt(int64_t vmax, int64_t* mismatches);
+/* Host-only inspection of the packed per-problem record the evaluation kernels read (csrc/gtop_types.cuh): set-up of one
+ * path as gtop_problems_create_from_paths does it, no device involved.  layout = {m, ns_cap, nsp, npair, nit2, stride,
+ * off_dt, off_ns, off_tt, off_TQ, off_PL, off_LiTP, off_Linv, off_T, off_Rc, off_Rg}; rec may be NULL to query it. */
+int gtop_debug_pack_record(int32_t m, const double* waypoints, const gtop_params* params, double* rec, int64_t cap,
+                           int32_t layout[16]);
 
 /* ---------------------------------------------------------------- optimiser loop ---- */
 /* Replaces the solver call of GradTrajOptimizer::optimizeTrajectory (grad_traj_optimizer.cpp:135-195:

@@ -147,3 +147,54 @@ def test_two_rank_gloo_sharding_matches_unsharded(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29513", str(script)],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("m,ns", [(10, 30), (7, 30), (4, 29), (5, 32), (2, 7), (3, 45)])
+def test_pair_schedule_tables_of_the_record(gtop_lib_cpu, m, ns):
+    """The multi-start kernel walks segments in pairs with consecutively numbered samples; the record's TQ / PL tables
+    carry that schedule (csrc/gtop_types.cuh).  Host-only check of their structure against the plain sample table:
+    slot q = 4u + j of pair p holds sample q of segment 2p (q < ns_a) or q - ns_a of segment 2p+1; TQ = (dt, t, t^2..t^5),
+    idle slots zero; PL = dt * (phi_r(t), phi_r'(t)) for the slot's segment, the second segment's lanes of the mixed
+    iteration in the pair's extra record, zero for the other segment's lanes and for columns 6, 7."""
+    import ctypes as C
+    from grad_traj_optimization_b200 import api, fixtures as fx
+    L = gtop_lib_cpu
+    prm = api.make_params(dict(fx.PARAMS_OPTI, samples_per_segment=ns))
+    rng = fx.Rng(3 * m + ns)
+    wp = np.cumsum(np.concatenate([[[-8.0, 0.0, 2.0]], 0.8 + rng.uniform((m, 3))]), axis=0)
+    lay = (C.c_int32 * 16)()
+    dp = C.POINTER(C.c_double)
+    assert L.gtop_debug_pack_record(m, wp.ctypes.data_as(dp), C.byref(prm), None, 0, lay) == 0
+    (m_, ns_cap, nsp, npair, nit2, stride, o_dt, o_ns, o_tt, o_tq, o_pl, o_litp, o_linv, o_T, o_rc, o_rg) = list(lay)
+    assert (m_, ns_cap, npair, nit2) == (m, ns, (m + 1) // 2, (2 * ns + 3) // 4)
+    rec = np.zeros(stride)
+    assert L.gtop_debug_pack_record(m, wp.ctypes.data_as(dp), C.byref(prm), rec.ctypes.data_as(dp), stride, lay) == 0
+    dt, nsv = rec[o_dt:o_dt + m], rec[o_ns:o_ns + m].astype(int)
+    tt = rec[o_tt:o_tt + m * 5 * ns].reshape(m, 5, ns)
+    Linv = rec[o_linv:o_linv + 36 * m].reshape(m, 6, 6)
+    TQ = rec[o_tq:o_tq + npair * nit2 * 24].reshape(npair, nit2, 3, 4, 2)
+    PLt = rec[o_pl:o_pl + npair * (nit2 + 1) * 64].reshape(npair, nit2 + 1, 8, 4, 2)   # [.., g, j, (A,B)]
+    T = rec[o_T:o_T + m]
+    assert np.allclose(dt * ns, T, rtol=1e-15) and np.all(nsv >= 1) and np.all(nsv <= ns)
+    seen_tq = np.zeros(TQ.shape[:2] + (4,), bool)
+    exp_pl = np.zeros_like(PLt)
+    for s in range(m):
+        p, second = s // 2, s & 1
+        ns_first = nsv[s - 1] if second else nsv[s]
+        for k in range(nsv[s]):
+            q = ns_first + k if second else k
+            u, j = q // 4, q % 4
+            t = tt[s, 0, k]
+            pw = np.array([1.0, t, tt[s, 1, k], tt[s, 2, k], tt[s, 3, k], tt[s, 4, k]])
+            assert np.array_equal(TQ[p, u, :, j, :].ravel(), np.concatenate([[dt[s]], pw[1:]]))
+            seen_tq[p, u, j] = True
+            mixed_iter = (ns_first % 4 != 0) and u == ns_first // 4
+            recpl = nit2 if (second and mixed_iter) else u
+            for g in range(6):
+                r = (g + 3) % 6 if (s & 1) else g
+                a = sum(pw[i] * Linv[s, i, r] for i in range(6))
+                b = sum(i * pw[i - 1] * Linv[s, i, r] for i in range(1, 6))
+                exp_pl[p, recpl, g, j] = (dt[s] * a, dt[s] * b)
+    assert np.all(np.moveaxis(TQ, 2, 3)[~seen_tq] == 0.0)   # idle slots
+    assert np.allclose(PLt, exp_pl, rtol=1e-13, atol=1e-300)
+    assert np.all(PLt[exp_pl == 0.0] == 0.0)                # zeros exactly where nothing is scheduled
