@@ -222,10 +222,13 @@ k_eval_mma(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
       // the window of the ring read as shared-memory broadcasts.
       if (j < 3) {
         const int r = j, jj = 3 * (w - 1) + r;
-        const double* __restrict__ band = pr + PL.off_Rg + jj * 9;
-        double bnd[9];
+        const double2* __restrict__ band = reinterpret_cast<const double2*>(pr + PL.off_RgP + jj * 10);  // padded row
+        double bnd[10];
 #pragma unroll
-        for (int u = 0; u < 9; ++u) bnd[u] = __ldg(band + u);
+        for (int u = 0; u < 5; ++u) {
+          const double2 v = ldg_tab(band + u);
+          bnd[2 * u] = v.x, bnd[2 * u + 1] = v.y;
+        }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           double gs = 0.0;  // window = waypoints w-1, w, w+1 of axis a

@@ -81,6 +81,7 @@ inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 
 //                        first segment's waypoint rows in between.
 //   LiTP  [m][3][6][2]   (Linv[2p][r], Linv[2p+1][r]): coefficient step, two powers per 128-bit load
 //   T     [m]            segment times T_s (segment_time, grad_traj_optimizer.cpp:73-81): post-hoc metrics kernel
+//   RgP   [3m-3][10]     the rows of Rg padded to 80 bytes: five aligned 128-bit loads per row in k_eval_mma
 struct ProbLayout {
   int m;       // segments
   int P;       // free derivatives per axis = 3(m-1)
@@ -90,7 +91,7 @@ struct ProbLayout {
   int npair;   // segment pairs = ceil(m/2)
   int nit2;    // iterations of k_eval_mma per pair at full sample count = ceil(2 ns_cap / 4)
   int off_dt, off_ns, off_Linv, off_tt, off_Rc, off_Rg, off_Df, off_LinvT;
-  int off_LiTP, off_TQ, off_PL, off_T;
+  int off_LiTP, off_TQ, off_PL, off_T, off_RgP;
   int stride;
 };
 
@@ -123,6 +124,8 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   L.off_TQ = o, o += L.npair * L.nit2 * 24;
   L.off_PL = o, o += L.npair * (L.nit2 + 1) * 64;
   L.off_T = o, o += m;
+  o = (o + 1) & ~1;
+  L.off_RgP = o, o += (3 * m - 3) * 10;
   L.stride = (o + 7) & ~7;  // keep every record 64-byte aligned
   return L;
 }

@@ -179,6 +179,8 @@ void pack_record(const ProblemHost& p, double* rec) {
   std::memcpy(rec + L.off_Rg, p.Rg.data(), sizeof(double) * p.Rg.size());
   std::memcpy(rec + L.off_Df, p.Df.data(), sizeof(double) * 18);
   std::memcpy(rec + L.off_T, p.seg_time.data(), sizeof(double) * p.m);
+  for (int i = 0; i < 3 * p.m - 3; ++i)
+    for (int j = 0; j < 9; ++j) rec[L.off_RgP + i * 10 + j] = p.Rg[(size_t)i * 9 + j];
   for (int s = 0; s < p.m; ++s)
     for (int i = 0; i < 6; ++i)
       for (int r = 0; r < 6; ++r) rec[L.off_LinvT + s * 36 + r * 6 + i] = p.Linv[(size_t)s * 36 + i * 6 + r];

@@ -86,7 +86,10 @@ __global__ void __launch_bounds__(128) k_setup_problems(SetupArgs A) {
     rec[L.off_LiTP + s * 36 + ((i >> 1) * 6 + r) * 2 + (i & 1)] = v;
   }
   for (int e = threadIdx.x; e < nd * 9; e += blockDim.x) rec[L.off_Rc + e] = setup_Rc_entry(Mseg, m, e / 9, e % 9);
-  for (int e = threadIdx.x; e < P * 9; e += blockDim.x) rec[L.off_Rg + e] = setup_Rg_entry(Mseg, m, e / 9, e % 9);
+  for (int e = threadIdx.x; e < P * 9; e += blockDim.x) {
+    const double v = setup_Rg_entry(Mseg, m, e / 9, e % 9);
+    rec[L.off_Rg + e] = v, rec[L.off_RgP + (e / 9) * 10 + e % 9] = v;
+  }
   // Df (getInitialD, qp_generator.cpp:410-431): start / end position, zero start / end velocity and acceleration
   if (threadIdx.x < 3) {
     const int a = threadIdx.x;
