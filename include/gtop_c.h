@@ -22,6 +22,13 @@
  *   gtop_objective             GradTrajOptimizer::costFunc (NLopt callback)         src/grad_traj_optimizer.cpp:554-562,
  *                              registered by set_min_objective(costFunc, this)      src/grad_traj_optimizer.cpp:140
  *   gtop_coeff_from_x          GradTrajOptimizer::getCoefficientFromDerivative      src/grad_traj_optimizer.cpp:253-279
+ *   gtop_sdf_reset_range       SDFMap::resetBuffer(min_pos, max_pos)                src/sdf_map.cpp:28-53
+ *   gtop_sdf_set_update_range  SDFMap::setUpdateRange(min_pos, max_pos)             src/sdf_map.cpp:244-264
+ *   gtop_sdf_query_dynamic     EDTEnvironment::evaluateEDTWithGrad / evaluateCoarseEDT   src/edt_environment.cpp:75-137
+ *   gtop_problems_create_from_paths_device / _from_kino_device   setPath / setKinoPath for a batch, on the device
+ *   gtop_solve_batch_device / _host, gtop_mma_minimize   the nlopt::opt(LD_MMA) call of optimizeTrajectory   src/grad_traj_optimizer.cpp:135-195
+ *   gtop_traj_metrics_device / _host   PolynomialTraj evaluation of the result      src/opti_node.cpp:104-144,
+ *                                                                                   include/grad_traj_optimization/polynomial_traj.hpp:70-203
  *
  * Conventions
  *   - every function returns 0 on success, <0 on error (GTOP_E_*); gtop_last_error() gives the
