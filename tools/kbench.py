@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Quick kernel iteration loop (GPU box): times k_eval_traj on the config-3 batch and checks a slice against the
+"""Quick kernel iteration loop (GPU box): times the evaluation kernel on the config-3 batch and checks a slice against the
 oracle.  Not the judged benchmark (that is bench.py).   python tools/kbench.py [--m 10] [--ns 30] [--sets 64] [--starts 1024]"""
 import argparse
 import os
