@@ -53,6 +53,34 @@ def test_no_cpu_fallback_without_device():
     assert rc != 0
 
 
+def test_new_entry_points_reject_bad_arguments_and_never_fall_back():
+    """Argument checks of the entry points added for SURVEY §8f run before any device work; without a device the
+    computing ones fail with an error code (no CPU fallback)."""
+    L = _capi.lib()
+    dp = C.POINTER(C.c_double)
+    z3 = (C.c_double * 3)(0, 0, 0)
+    assert L.gtop_traj_metrics_host(None, z3, 1, 0, 1, z3) < 0 and b"null" in L.gtop_last_error()
+    assert L.gtop_sdf_query_dynamic(None, None, 0, 0.0, z3, 1, z3, z3, None) < 0
+    assert L.gtop_sdf_set_update_range(None, z3, z3) < 0 and L.gtop_sdf_reset_range(None, z3, z3) < 0
+    lay = (C.c_int32 * 16)()
+    p = _capi.GtopParams()
+    L.gtop_params_default(C.byref(p))
+    w = np.zeros((3, 3))
+    w[:, 0] = [0, 1, 2]
+    assert L.gtop_debug_pack_record(1, w.ctypes.data_as(dp), C.byref(p), None, 0, lay) < 0           # m >= 2
+    assert L.gtop_debug_pack_record(2, w.ctypes.data_as(dp), C.byref(p), None, 0, lay) == 0
+    rec = np.zeros(8)
+    assert L.gtop_debug_pack_record(2, w.ctypes.data_as(dp), C.byref(p), rec.ctypes.data_as(dp), 8, lay) < 0  # buffer too small
+    bad = np.zeros((3, 3))  # coincident waypoints: zero segment time
+    rec = np.zeros(lay[5])
+    assert L.gtop_debug_pack_record(2, bad.ctypes.data_as(dp), C.byref(p), rec.ctypes.data_as(dp), lay[5], lay) < 0
+    assert b"segment time" in L.gtop_last_error()
+    if L.gtop_device_count() == 0:
+        h = C.c_void_p()
+        rc = L.gtop_problems_create_from_paths_device(1, 2, w.ctypes.data_as(dp), C.byref(p), 0, C.byref(h))
+        assert rc != 0 and b"no CPU fallback" in L.gtop_last_error()
+
+
 def test_product_package_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under grad_traj_optimization_b200/ or include/ may reference it."""
     bad = []
