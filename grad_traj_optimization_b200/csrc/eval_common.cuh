@@ -56,8 +56,15 @@ constexpr int kExpTab = 16;
 // compiler re-materialises each 64-bit constant with two UMOVs per use)
 __constant__ double kExp2Poly[6] = {1.5403530393381609e-4, 1.3333558146428443e-3, 9.6181291076284772e-3,
                                     5.5504108664821580e-2, 2.4022650695910071e-1, 6.9314718055994531e-1};
+// 2^(j/16), correctly rounded (a copy in shared memory serves the lanes' different j in one wavefront; the constant
+// bank would serialise them)
+__constant__ double kExp2Tab[kExpTab] = {
+    0x1.0000000000000p+0, 0x1.0b5586cf9890fp+0, 0x1.172b83c7d517bp+0, 0x1.2387a6e756238p+0,
+    0x1.306fe0a31b715p+0, 0x1.3dea64c123422p+0, 0x1.4bfdad5362a27p+0, 0x1.5ab07dd485429p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.7a11473eb0187p+0, 0x1.8ace5422aa0dbp+0, 0x1.9c49182a3f090p+0,
+    0x1.ae89f995ad3adp+0, 0x1.c199bdd85529cp+0, 0x1.d5818dcfba487p+0, 0x1.ea4afa2a490dap+0};
 __device__ __forceinline__ void exp2_tab_init(double* T, int tid, int nthreads) {
-  for (int i = tid; i < kExpTab; i += nthreads) T[i] = exp2((double)i * (1.0 / kExpTab));
+  for (int i = tid; i < kExpTab; i += nthreads) T[i] = kExp2Tab[i];
 }
 __device__ __forceinline__ double exp2_tab(double y, const double* __restrict__ T) {
   const double kMagic = 422212465065984.0;  // 1.5 * 2^48: ulp = 1/16

@@ -57,7 +57,7 @@ inline int64_t quad_elems(int nx, int ny, int nz) { return (int64_t)((nx + 1) / 
 //                        reference's pow calls, :457-485,549)
 //   Rc    [3m+3][9]      column band of R in waypoint order (smoothness cost, :326-327)
 //   Rg    [3m-3][9]      band of (2 Rfp^T df + 2 Rpp dp) rows (smoothness gradient, :330-332)
-//   Df    [3][6]         fixed derivatives per axis: p0,v0,a0,pEnd,vEnd,aEnd
+//   Df    [3][6]         fixed derivatives per axis: p0,v0,a0,pEnd,vEnd,aEnd (16-byte aligned)
 //   LinvT [m][6][6]      transpose of Linv (col = power): the coefficient step reads 6 contiguous
 //                        doubles per derivative instead of a stride-6 column
 // Sections read by the multi-start kernel k_eval_mma (eval_mma_kernel.cu).  The kernel walks the segments in PAIRS
@@ -112,6 +112,7 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   L.off_tt = o, o += m * 5 * ns_cap;
   L.off_Rc = o, o += (3 * m + 3) * 9;
   L.off_Rg = o, o += (3 * m - 3) * 9;
+  o = (o + 1) & ~1;  // 16-byte aligned: k_eval_mma_pairs fetches Df with a bulk copy
   L.off_Df = o, o += 18;
   L.off_LinvT = o, o += m * 36;
   o = (o + 1) & ~1;

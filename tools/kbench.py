@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--starts", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--check", type=int, default=256)
+    ap.add_argument("--bufs", type=int, default=4, help="rotating X / grad / cost buffer sets (working set > L2)")
     args = ap.parse_args()
     import torch
     from grad_traj_optimization_b200 import api, fixtures as fx
@@ -33,18 +34,18 @@ def main():
     x0, (lb, ub) = ps.x0(), ps.bounds()
     X = np.concatenate([fx.multi_starts(x0[p], lb[p], ub[p], args.starts, seed=7 + p) for p in range(args.sets)])
     B, n = X.shape
-    Xd = [torch.from_numpy(X).cuda() for _ in range(4)]
-    Gd = [torch.empty_like(Xd[0]) for _ in range(4)]
-    Cd = [torch.empty(B, dtype=torch.float64, device="cuda") for _ in range(4)]
+    Xd = [torch.from_numpy(X).cuda() for _ in range(args.bufs)]
+    Gd = [torch.empty_like(Xd[0]) for _ in range(args.bufs)]
+    Cd = [torch.empty(B, dtype=torch.float64, device="cuda") for _ in range(args.bufs)]
     stream = torch.cuda.Stream()  # explicit stream: a NULL stream means "the handle's own stream" to the library
     st = stream.cuda_stream
     for i in range(5):
-        ps.eval_device(gm, Xd[i % 4], Cd[i % 4], Gd[i % 4], starts_per_problem=args.starts, stream=st)
+        ps.eval_device(gm, Xd[i % args.bufs], Cd[i % args.bufs], Gd[i % args.bufs], starts_per_problem=args.starts, stream=st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.iters):
-        ps.eval_device(gm, Xd[i % 4], Cd[i % 4], Gd[i % 4], starts_per_problem=args.starts, stream=st)
+        ps.eval_device(gm, Xd[i % args.bufs], Cd[i % args.bufs], Gd[i % args.bufs], starts_per_problem=args.starts, stream=st)
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
