@@ -314,17 +314,11 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
   }
 }
 
-bool eval_mma_applicable(const ProbLayout& PL, int64_t traj_offset, int64_t starts_per_problem);
+bool eval_mma_applicable(const ProbLayout& PL, int64_t B, int num_problems, int64_t starts_per_problem);
 cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
                             const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
                             int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
                             cudaStream_t stream);
-
-bool eval_mma_pairs_applicable(const ProbLayout& PL, int64_t B, int num_problems, int64_t starts_per_problem);
-cudaError_t launch_eval_mma_pairs(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
-                                  const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
-                                  int64_t starts_per_problem, double* cost, double* grad,
-                                  unsigned long long* oob_counter, cudaStream_t stream);
 
 // GTOP_EVAL_KERNEL=general forces the quarter-warp kernel (tests exercise both); default: the DMMA
 // multi-start kernel whenever groups of 8 consecutive trajectories share a problem.
@@ -342,11 +336,7 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
                         int max_ctas, cudaStream_t stream) {
   (void)max_ctas;
   if (B <= 0) return cudaSuccess;
-  static const bool mma_v1 = [] { const char* e = std::getenv("GTOP_MMA_V"); return e && std::atoi(e) == 1; }();
-  if (!force_general() && !E.vel_acc && !mma_v1 && PL.m >= 2 && eval_mma_pairs_applicable(PL, B, num_problems, starts_per_problem))
-    return launch_eval_mma_pairs(S, PL, prob, num_problems, E, X, B, traj_offset, starts_per_problem, cost, grad,
-                                 oob_counter, stream);
-  if (!force_general() && !E.vel_acc && eval_mma_applicable(PL, traj_offset, starts_per_problem))
+  if (!force_general() && !E.vel_acc && eval_mma_applicable(PL, B, num_problems, starts_per_problem))
     return launch_eval_mma(S, PL, prob, num_problems, E, X, B, traj_offset, starts_per_problem, cost, grad, oob_counter,
                            stream);
   // warps per CTA: as many as keep the CTA's shared memory modest (4 CTAs/SM at 16 warps/SM)

@@ -112,7 +112,7 @@ inline ProbLayout make_layout(int m, int ns_cap) {
   L.off_tt = o, o += m * 5 * ns_cap;
   L.off_Rc = o, o += (3 * m + 3) * 9;
   L.off_Rg = o, o += (3 * m - 3) * 9;
-  o = (o + 1) & ~1;  // 16-byte aligned: k_eval_mma_pairs fetches Df with a bulk copy
+  o = (o + 1) & ~1;  // 16-byte aligned: k_eval_mma fetches Df with a bulk copy
   L.off_Df = o, o += 18;
   L.off_LinvT = o, o += m * 36;
   o = (o + 1) & ~1;

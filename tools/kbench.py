@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--starts", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--check", type=int, default=256)
+    ap.add_argument("--step", type=int, default=2, help="1 = OPT_FIRST_STEP (collision only), 2 = OPT_SECOND_STEP")
+    ap.add_argument("--dump", default="", help="save cost / gradient of the first buffer set to this .npz")
     ap.add_argument("--bufs", type=int, default=4, help="rotating X / grad / cost buffer sets (working set > L2)")
     args = ap.parse_args()
     import torch
@@ -40,18 +42,20 @@ def main():
     stream = torch.cuda.Stream()  # explicit stream: a NULL stream means "the handle's own stream" to the library
     st = stream.cuda_stream
     for i in range(5):
-        ps.eval_device(gm, Xd[i % args.bufs], Cd[i % args.bufs], Gd[i % args.bufs], starts_per_problem=args.starts, stream=st)
+        ps.eval_device(gm, Xd[i % args.bufs], Cd[i % args.bufs], Gd[i % args.bufs], starts_per_problem=args.starts, stream=st, step=args.step)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.iters):
-        ps.eval_device(gm, Xd[i % args.bufs], Cd[i % args.bufs], Gd[i % args.bufs], starts_per_problem=args.starts, stream=st)
+        ps.eval_device(gm, Xd[i % args.bufs], Cd[i % args.bufs], Gd[i % args.bufs], starts_per_problem=args.starts, stream=st, step=args.step)
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
     bytes_eval = args.m * args.ns * 64 + 16 * n + 8
     print("m=%d ns=%d B=%d: %.4f ms/batch, %.3e evals/s, %.1f GB/s algorithmic = %.1f%% of 6552.3" % (
         args.m, args.ns, B, ms, B / ms * 1e3, B * bytes_eval / ms / 1e6, B * bytes_eval / ms / 1e6 / 65.523))
+    if args.dump:
+        np.savez(args.dump, cost=Cd[0].cpu().numpy(), grad=Gd[0].cpu().numpy())
     if args.check:
         from common import oracle_problem, rel_cost_err, rel_grad_err
         from oracle import OracleMap
@@ -63,7 +67,7 @@ def main():
         for p in (range(args.sets) if full else (0, args.sets - 1)):
             opt = oracle_problem(prm, om, wps[p])
             sl = slice(p * args.starts, p * args.starts + min(args.check, args.starts))
-            cr, gr, _, _ = opt.eval_batch(X[sl], 2)
+            cr, gr, _, _ = opt.eval_batch(X[sl], args.step)
             ec, eg = max(ec, rel_cost_err(c[sl], cr).max()), max(eg, rel_grad_err(g[sl], gr).max())
         print("parity vs oracle%s: cost %.2e grad %.2e %s" % (" (all %d trajectories)" % B if full else "", ec, eg,
                                                              "OK" if max(ec, eg) <= 1e-9 else "FAIL"))
