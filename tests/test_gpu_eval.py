@@ -280,3 +280,44 @@ def test_velocity_acceleration_penalty_flag(gtop_lib, starts):
         c1, g1 = obj(X[1])
         assert abs(c1 - c_ref[1]) <= TOL * abs(c_ref[1]) and rel_grad_err(g1, g_ref[1]).max() <= TOL
         obj.close()
+
+
+def test_full_config3_batch_parity(gtop_lib):
+    """BASELINE configs[2] at full size: all 65,536 trajectories (64 waypoint sets x 1,024 starts, m = 10) against the
+    oracle (a few seconds on the host cores), plus the 8,192-trajectory shards a rank gets at 8 GPUs: bit-identical rows."""
+    api = _api()
+    om, _ = map_a_oracle()
+    gm = _gpu_map_from_oracle(om)
+    wps, X = map_a_batch(10, 64, 1024)
+    ps = api.ProblemSet.from_paths(wps, api.make_params(fx.PARAMS_OPTI))
+    c, g, oob = ps.eval_host(gm, X, step=2, starts_per_problem=1024)
+    assert oob == 0
+    ec = eg = 0.0
+    for p in range(64):
+        opt = oracle_problem(fx.PARAMS_OPTI, om, wps[p])
+        sl = slice(1024 * p, 1024 * (p + 1))
+        cr, gr, _, _ = opt.eval_batch(X[sl], 2)
+        ec, eg = max(ec, rel_cost_err(c[sl], cr).max()), max(eg, rel_grad_err(g[sl], gr).max())
+    assert ec <= TOL and eg <= TOL, (ec, eg)
+    for r in (0, 3, 7):  # strong-scaling shards: same bits as the full batch
+        sl = slice(8192 * r, 8192 * (r + 1))
+        cs, gs, _ = ps.eval_host(gm, X[sl], step=2, starts_per_problem=1024, traj_offset=8192 * r)
+        assert np.array_equal(cs, c[sl]) and np.array_equal(gs, g[sl])
+
+
+def test_config5_batch_parity(gtop_lib):
+    """BASELINE configs[4] shape: m = 30, 200 samples per segment; 2 waypoint sets x 1,024 starts against the oracle."""
+    api = _api()
+    om, dist = map_a_oracle()
+    gm = _gpu_map_from_oracle(om)
+    prm = dict(fx.PARAMS_OPTI, samples_per_segment=200)
+    wps = np.stack([fx.random_waypoints(p, 30, dist, fx.MAP_A["map_origin"], fx.MAP_A["resolution"]) for p in range(2)])
+    ps = api.ProblemSet.from_paths(wps, api.make_params(prm))
+    x0, (lb, ub) = ps.x0(), ps.bounds()
+    X = np.concatenate([fx.multi_starts(x0[p], lb[p], ub[p], 1024, seed=7 + p) for p in range(2)])
+    c, g, oob = ps.eval_host(gm, X, step=2, starts_per_problem=1024)
+    for p in range(2):
+        opt = oracle_problem(prm, om, wps[p])
+        sl = slice(1024 * p, 1024 * (p + 1))
+        cr, gr, oob_ref, _ = opt.eval_batch(X[sl], 2)
+        assert rel_cost_err(c[sl], cr).max() <= TOL and rel_grad_err(g[sl], gr).max() <= TOL

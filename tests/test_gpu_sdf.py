@@ -69,6 +69,37 @@ def test_edt_random_small_grids_vs_bruteforce(gtop_lib, dims, nocc, seed):
     assert np.array_equal(d_gpu, om.brute_edt())
 
 
+@pytest.mark.parametrize("dims,nocc,seed,windowed", [
+    # rows longer than every template bucket of the y / x passes of csrc/sdf_kernels.cu: <= 2048 (the 2000-voxel rows of
+    # BASELINE config 4), <= 4096, <= 16384 (64-bit intersection arithmetic above 8192), on both row axes
+    ((2000, 8, 8), 40, 21, False), ((8, 2000, 8), 40, 22, False), ((4000, 4, 4), 30, 23, False), ((4, 4000, 4), 30, 24, False),
+    ((9000, 2, 2), 25, 25, False), ((2, 9000, 2), 25, 26, False), ((2000, 8, 8), 40, 27, True), ((4, 4000, 4), 30, 28, True),
+    ((9000, 2, 2), 25, 29, True), ((2000, 3, 5), 1, 30, False), ((2000, 2, 2), 6000, 31, False)])
+def test_edt_long_rows_vs_oracle_and_bruteforce(gtop_lib, dims, nocc, seed, windowed):
+    """sdf_map.cpp:266-368 on grids whose x / y rows are as long as the large map's (and longer)."""
+    res = 0.25  # (dims * res is exact in binary: ceil(size / res) gives back dims)
+    size = np.array(dims, dtype=np.float64) * res
+    origin = np.array([-3.0, 1.0, 0.0])
+    rng = fx.Rng(seed)
+    idx = np.stack([np.floor(rng.uniform((nocc,)) * d).astype(int) for d in dims], axis=1)
+    occ = np.zeros(dims, dtype=np.int32)
+    occ[idx[:, 0], idx[:, 1], idx[:, 2]] = 1
+    om = OracleMap(origin, res, size)
+    assert om.grid == tuple(dims)
+    gm = _gpu_map(origin, res, size)
+    om.set_occupancy_buffer(occ), gm.upload_occupancy(occ)
+    if windowed:  # setUpdateRange over most of the long axis, then a full rebuild on top (min with the old field)
+        lo, hi = origin + 0.1 * size, origin + 0.93 * size
+        for mp in (om, gm):
+            mp.set_update_range(lo, hi), mp.update_esdf()
+        assert np.array_equal(gm.distance(), om.distance())
+    for mp in (om, gm):
+        mp.update_esdf()
+    d_gpu = gm.distance()
+    assert np.array_equal(d_gpu, om.distance())
+    assert np.array_equal(d_gpu, om.brute_edt())
+
+
 def test_edt_empty_map_is_10000_everywhere(gtop_lib):
     gm = _gpu_map([0, 0, 0], 0.5, [8, 6, 4])
     gm.reset()
