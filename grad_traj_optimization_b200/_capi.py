@@ -14,7 +14,7 @@ SYMBOLS = (
     "gtop_abi_version", "gtop_last_error", "gtop_device_count", "gtop_params_default", "gtop_host_alloc",
     "gtop_host_free", "gtop_sdf_create", "gtop_sdf_destroy", "gtop_sdf_grid", "gtop_sdf_reset",
     "gtop_sdf_reset_range", "gtop_sdf_set_update_range", "gtop_sdf_update_range",
-    "gtop_sdf_set_occupancy", "gtop_sdf_set_occupancy_boxes", "gtop_sdf_update_esdf", "gtop_sdf_last_edt_ms",
+    "gtop_sdf_set_occupancy", "gtop_sdf_set_occupancy_boxes", "gtop_sdf_update_esdf", "gtop_sdf_last_edt_ms", "gtop_sdf_last_update_ms", "gtop_sdf_gather_layout",
     "gtop_sdf_download_distance", "gtop_sdf_upload_distance", "gtop_sdf_download_occupancy",
     "gtop_sdf_upload_occupancy", "gtop_sdf_distance_device_ptr", "gtop_sdf_query", "gtop_sdf_query_dynamic", "gtop_problems_create_dense",
     "gtop_problems_create_from_paths", "gtop_problems_create_from_kino", "gtop_problems_create_from_paths_device",
@@ -72,6 +72,8 @@ def lib():
         "gtop_sdf_set_occupancy_boxes": (C.c_int, [vp, C.POINTER(i32), i64]),
         "gtop_sdf_update_esdf": (C.c_int, [vp]),
         "gtop_sdf_last_edt_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "gtop_sdf_last_update_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "gtop_sdf_gather_layout": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i64)]),
         "gtop_sdf_download_distance": (C.c_int, [vp, dp]),
         "gtop_sdf_upload_distance": (C.c_int, [vp, dp]),
         "gtop_sdf_download_occupancy": (C.c_int, [vp, C.POINTER(i32)]),

@@ -108,6 +108,18 @@ class SdfMap:
         check(lib().gtop_sdf_last_edt_ms(self.h, ms))
         return [float(v) for v in ms]
 
+    def last_update_ms(self):
+        """z, y, x passes, their sum, rebuild of the gather copy, update start -> ready for the evaluation kernels."""
+        ms = (C.c_float * 6)()
+        check(lib().gtop_sdf_last_update_ms(self.h, ms))
+        return [float(v) for v in ms]
+
+    def gather_layout(self):
+        """(has_quad_copy, resident device bytes): see gtop_sdf_gather_layout."""
+        q, b = C.c_int32(0), C.c_int64(0)
+        check(lib().gtop_sdf_gather_layout(self.h, C.byref(q), C.byref(b)))
+        return bool(q.value), int(b.value)
+
     def distance(self):
         out = np.empty(self.nvox, dtype=np.float64)
         check(lib().gtop_sdf_download_distance(self.h, _dp(out)))

@@ -133,7 +133,10 @@ struct SdfCell {
   bool special;  // !in_map || xlow || ylow: needs the select path of sdf_finish (rare: map border)
 };
 
-template <bool kNoAlloc>
+// kPlain: the map keeps no quad copy (maps too big for one: the copy is 4x the field and has to be rebuilt after every
+// update): the eight corners come straight from `dist`, z fastest — eight 64-bit loads from four 32-byte sectors where
+// the quad copy needs two 256-bit loads from two; same values, same clamping.
+template <bool kNoAlloc, bool kPlain = false>
 __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double py, double pz, float fx32, float fy32,
                                            float fz32, SdfCell& c) {
   // isInMap (:55-69) on the float images of the bounds: exact for float-valued positions
@@ -161,12 +164,18 @@ __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double p
   // the clamps also keep the loads of an out-of-map sample inside the buffer: no branch needed
   const int x0 = max(min(ix, S.nx - 1), 0), y0 = max(min(iy, S.ny - 1), 0);
   const int z0 = max(min(iz, S.nz - 1), 0), z1 = max(min(iz + 1, S.nz - 1), 0);
+  if (kPlain) {
+    const int x1 = min(x0 + 1, S.nx - 1), y1 = min(y0 + 1, S.ny - 1), dz = z1 - z0;
+    const double* __restrict__ r00 = S.dist + ((size_t)x0 * S.ny + y0) * S.nz + z0;
+    const double* __restrict__ r01 = S.dist + ((size_t)x0 * S.ny + y1) * S.nz + z0;
+    const double* __restrict__ r10 = S.dist + ((size_t)x1 * S.ny + y0) * S.nz + z0;
+    const double* __restrict__ r11 = S.dist + ((size_t)x1 * S.ny + y1) * S.nz + z0;
+    c.q0.v00 = __ldg(r00), c.q0.v01 = __ldg(r01), c.q0.v10 = __ldg(r10), c.q0.v11 = __ldg(r11);
+    c.q1.v00 = __ldg(r00 + dz), c.q1.v01 = __ldg(r01 + dz), c.q1.v10 = __ldg(r10 + dz), c.q1.v11 = __ldg(r11 + dz);
+    return;
+  }
   const int e0 = ((((x0 >> 1) * S.nyh + (y0 >> 1)) * S.nz + z0) << 2) + ((x0 & 1) << 1) + (y0 & 1);
-#ifdef GTOP_EXP_NOGATHER  // timing experiment only: every lane reads the same two lines
-  const char* p = (const char*)S.quad + (size_t)(unsigned)(e0 & 3) * 32u;
-#else
   const char* p = (const char*)S.quad + (size_t)(unsigned)e0 * 32u;
-#endif
   c.q0 = ldg_quad<kNoAlloc>(p);
   c.q1 = ldg_quad<kNoAlloc>(p + (z1 - z0) * 128);
 }
@@ -211,7 +220,7 @@ __device__ __forceinline__ void sdf_finish(const SdfCell& c, double& dist, doubl
 // segment's coefficients `cb` (c[3][6] then e[3][4] = k*c_k), trilinear SDF, penalties, and the sample's
 // contribution to the 20 per-segment sums v[] (U[a][i] at a*6+i, cost at 18, velocity/acceleration penalty cost
 // at 19).  Shared by the general kernel and the single-trajectory kernel.
-template <bool kVelAcc, bool kWarpUniform>
+template <bool kVelAcc, bool kWarpUniform, bool kPlain = false>
 __device__ __forceinline__ void sample_accumulate(const SdfView S, const EvalScalars E, const double kA,
                                                   const double* __restrict__ cb, double t, double t2, double t3, double t4,
                                                   double t5, const double* __restrict__ xtab, double (&v)[20],
@@ -231,7 +240,7 @@ __device__ __forceinline__ void sample_accumulate(const SdfView S, const EvalSca
     pos[a] = (double)pf[a];
   }
   SdfCell cell;
-  sdf_gather<false>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
+  sdf_gather<false, kPlain>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const double* c = cb + a * 6;

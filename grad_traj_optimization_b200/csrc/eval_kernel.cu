@@ -70,7 +70,8 @@ __host__ __device__ inline int traj_smem_doubles(int m) { return 2 * 9 * (m + 1)
 // kVelAcc: also evaluate the velocity / acceleration penalty block that upstream HEAD has commented out
 // (:383-407, penalties :517-535) — gtop_params.vel_acc_penalty, default off; literal restatement including
 // the `cv` / `ca` values carried from the k = 2 iteration of the cost loop into the gradient loop.
-template <bool kVelAcc>
+// kPlain: the map keeps no quad copy; corners come straight from the distance field (eval_common.cuh).
+template <bool kVelAcc, bool kPlain>
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, GTOP_EVAL_MINB)
 k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_problems, EvalScalars E,
             const double* __restrict__ X, int64_t B, int64_t traj_offset, int64_t starts_per_problem,
@@ -170,7 +171,7 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
           pos[a] = (double)pf[a];
         }
         SdfCell cell;
-        sdf_gather<false>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
+        sdf_gather<false, kPlain>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const double* c = cb + a * 6;
@@ -344,7 +345,9 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
   int wpc = kMaxWarpsPerCta;
   while (wpc > 1 && per_warp * wpc + 512 > 48 * 1024) wpc >>= 1;
   const size_t smem = per_warp * wpc + kExpTab * sizeof(double);
-  auto kern = E.vel_acc ? k_eval_traj<true> : k_eval_traj<false>;
+  const bool plain = S.quad == nullptr;
+  auto kern = E.vel_acc ? (plain ? k_eval_traj<true, true> : k_eval_traj<true, false>)
+                        : (plain ? k_eval_traj<false, true> : k_eval_traj<false, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -184,8 +184,17 @@ __device__ __forceinline__ unsigned atom_add_acq_rel_cta(unsigned* p, unsigned v
 
 // kNoAlloc: L1 policy of the gathers (see ldg_quad), chosen from the sampling density.  kOneRound: as many warps as
 // pairs (no loop around the pair body: the compiler then keeps the sample loop's ~40 map / penalty constants in uniform
-// registers instead of re-reading them from the constant bank in every iteration).
-template <bool kNoAlloc, bool kOneRound, bool kHorner>
+// registers instead of re-reading them from the constant bank in every iteration).  kPlain: the map keeps no quad copy.
+// GTOP_POLY_HORNER (compile-time experiment, not built by default): position / velocity polynomials by Horner's rule
+// with FMA — 27 FP64 instructions per sample less and one 128-bit table load instead of three (0.317 ms against
+// 0.335 ms per 65,536, profiles/r2_microbench.md) — but the float image of a position is then no longer the
+// reference's in ~13 of 20 million samples, and such a flip moves that sample's penalty by 1e-6 relative.
+#ifdef GTOP_POLY_HORNER
+constexpr bool kHorner = true;
+#else
+constexpr bool kHorner = false;
+#endif
+template <bool kNoAlloc, bool kOneRound, bool kPlain>
 __global__ void __launch_bounds__(kPairMaxWarps * 32, 2)
 k_eval_mma(SdfView S, ProbLayout PL, PairSmem sm, const double* __restrict__ prob, unsigned num_problems,
                  EvalScalars E, const double* __restrict__ X, int64_t B, int head, unsigned group0, unsigned gpp,
@@ -352,7 +361,7 @@ k_eval_mma(SdfView S, ProbLayout PL, PairSmem sm, const double* __restrict__ pro
             pos[a] = (double)pf[a];
           }
           SdfCell cell;
-          sdf_gather<kNoAlloc>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
+          sdf_gather<kNoAlloc, kPlain>(S, pos[0], pos[1], pos[2], pf[0], pf[1], pf[2], cell);  // 2 x LDG.256 in flight from here
 #pragma unroll
           for (int a = 0; a < 3; ++a) {
             const double2 e01 = cf[a * 5 + 3], e23 = cf[a * 5 + 4];
@@ -579,11 +588,12 @@ cudaError_t launch_eval_mma(const SdfView& S, const ProbLayout& PL, const double
   const PairSmem sm = pair_smem(PL.m, W);
   const size_t smem = sizeof(double) * (size_t)sm.total;
   const bool one = W == PL.npair;
-  static const bool horner = [] { const char* e = std::getenv("GTOP_POLY_HORNER"); return e && std::atoi(e) != 0; }();  // experiment
-  auto kern = PL.ns_cap <= 64 ? (one ? k_eval_mma<true, true, false> : k_eval_mma<true, false, false>)
-                              : (one ? k_eval_mma<false, true, false> : k_eval_mma<false, false, false>);
-  if (horner) kern = PL.ns_cap <= 64 ? (one ? k_eval_mma<true, true, true> : k_eval_mma<true, false, true>)
-                                     : (one ? k_eval_mma<false, true, true> : k_eval_mma<false, false, true>);
+  const bool na = PL.ns_cap <= 64;
+  auto kern = k_eval_mma<false, false, false>;
+  if (S.quad == nullptr) kern = na ? (one ? k_eval_mma<true, true, true> : k_eval_mma<true, false, true>)
+                                   : (one ? k_eval_mma<false, true, true> : k_eval_mma<false, false, true>);
+  else kern = na ? (one ? k_eval_mma<true, true, false> : k_eval_mma<true, false, false>)
+                 : (one ? k_eval_mma<false, true, false> : k_eval_mma<false, false, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

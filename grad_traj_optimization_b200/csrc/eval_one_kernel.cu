@@ -22,7 +22,7 @@ constexpr int kOneMaxSegments = 16;  // one warp per segment; 512 threads keep 1
 // shared memory (doubles): Wd[3][nrow] | gseg[m][18] | jc[m] | jva[m] | cb[m][32] | xtab[16] ; then oob counters
 __host__ __device__ inline int one_smem_doubles(int m) { return 9 * (m + 1) + 18 * m + 2 * m + 32 * m + kExpTab; }
 
-template <bool kVelAcc>
+template <bool kVelAcc, bool kPlain>
 __global__ void __launch_bounds__(kOneMaxSegments * 32)
 k_eval_one(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_problems, EvalScalars E,
            const double* __restrict__ X, int64_t B, int64_t traj_offset, int64_t starts_per_problem,
@@ -84,7 +84,7 @@ k_eval_one(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_pr
     for (int i = 0; i < 20; ++i) v[i] = 0.0;
     for (int k = lane; k < ns; k += 32) {
       const int nc = PL.ns_cap;
-      sample_accumulate<kVelAcc, false>(S, E, kA, cb, tt[k], tt[nc + k], tt[2 * nc + k], tt[3 * nc + k], tt[4 * nc + k], xtab,
+      sample_accumulate<kVelAcc, false, kPlain>(S, E, kA, cb, tt[k], tt[nc + k], tt[2 * nc + k], tt[3 * nc + k], tt[4 * nc + k], xtab,
                                         v, oob);
     }
     // ---- the 20 sums of the segment over its 32 lanes -------------------------------------------------
@@ -178,7 +178,9 @@ cudaError_t launch_eval_one(const SdfView& S, const ProbLayout& PL, const double
                             cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
   const size_t smem = sizeof(double) * (size_t)one_smem_doubles(PL.m);
-  auto kern = E.vel_acc ? k_eval_one<true> : k_eval_one<false>;
+  const bool plain = S.quad == nullptr;
+  auto kern = E.vel_acc ? (plain ? k_eval_one<true, true> : k_eval_one<true, false>)
+                        : (plain ? k_eval_one<false, true> : k_eval_one<false, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -97,12 +97,12 @@ struct gtop_sdf {
   double origin[3], map_size[3];
   int64_t nvox = 0;
   double* dist = nullptr;
-  void* quad = nullptr;  // xy-quad copy of dist (SdfView::quad), rebuilt whenever dist changes
+  void* quad = nullptr;  // xy-quad copy of dist (SdfView::quad), rebuilt whenever dist changes; nullptr for big maps
   uint8_t* occ = nullptr;
   int32_t *d1 = nullptr, *d2 = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  float last_ms[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // update start, after z, y, x, after the quad build
+  float last_ms[6] = {0, 0, 0, 0, 0, 0};                                // z, y, x, z+y+x, quad build, call to evaluator-ready
   bool dist_fresh = false;  // distance buffer is 10000 everywhere (just created / reset)
   // update window of the next gtop_sdf_update_esdf (SDFMap::min_vec / max_vec, sdf_map.cpp:13-14): voxel indices,
   // inclusive; the whole grid unless gtop_sdf_set_update_range was called since the last update (:366-367)
@@ -246,21 +246,32 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
   s->nvox = (int64_t)g[0] * g[1] * g[2];
   for (int i = 0; i < 3; ++i) s->win_lo[i] = 0, s->win_hi[i] = g[i] - 1;
   cudaError_t e = cudaMalloc(&s->dist, sizeof(double) * s->nvox);
-  if (e == cudaSuccess) e = cudaMalloc(&s->quad, 32 * (size_t)quad_elems(g[0], g[1], g[2]));
+  // The xy-quad copy (4x the field) halves the L1 wavefronts of a gather and pays while it stays cache-resident; a map
+  // whose copy would not (default: above 1 GiB) is gathered straight from `dist`: no 4x footprint, and no rebuild of the
+  // copy — more bytes than the whole EDT moves — between an update and the first evaluation.
+  const char* qenv = std::getenv("GTOP_QUAD_LIMIT_MB");  // read per map: tests build both layouts in one process
+  const double quad_limit_mb = qenv ? std::atof(qenv) : 1024.0;
+  const size_t quad_bytes = 32 * (size_t)quad_elems(g[0], g[1], g[2]);
+  const bool with_quad = (double)quad_bytes <= quad_limit_mb * 1048576.0;
+  if (e == cudaSuccess && with_quad) e = cudaMalloc(&s->quad, quad_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&s->occ, s->nvox);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+  for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
   if (e != cudaSuccess) {
     gtop_sdf_destroy(s);
     return fail(GTOP_E_ALLOC, std::string("sdf allocation: ") + cudaGetErrorString(e));
   }
   v.dist = s->dist;
   v.quad = s->quad;
-  CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));  // sdf_map.cpp:22-23
+  e = launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream);  // sdf_map.cpp:22-23
   s->dist_fresh = true;
-  CU(launch_build_quads(v, s->dist, s->quad, s->stream));
+  if (e == cudaSuccess && s->quad) e = launch_build_quads(v, s->dist, s->quad, s->stream);
   g_launches += 2;
-  CU(cudaStreamSynchronize(s->stream));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) {
+    gtop_sdf_destroy(s);
+    return fail(GTOP_E_CUDA, std::string("sdf initialisation: ") + cudaGetErrorString(e));
+  }
   *out = s;
   return GTOP_OK;
 }
@@ -288,7 +299,7 @@ int gtop_sdf_reset(gtop_sdf* s) {
   CU(cudaSetDevice(s->device));
   CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));
   s->dist_fresh = true;
-  CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
+  if (s->quad) CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   g_launches += 2;
   CU(cudaStreamSynchronize(s->stream));
   return GTOP_OK;
@@ -322,7 +333,7 @@ int gtop_sdf_reset_range(gtop_sdf* s, const double min_pos[3], const double max_
   CU(cudaSetDevice(s->device));
   const VoxelBox b = window_box(lo, hi);
   CU(launch_box_reset(s->dist, s->occ, b, s->view.ny, s->view.nz, 10000.0, s->stream));  // sdf_map.cpp:45-52
-  CU(launch_build_quads_box(s->view, s->dist, s->quad, b, s->stream));
+  if (s->quad) CU(launch_build_quads_box(s->view, s->dist, s->quad, b, s->stream));
   g_launches += 2;
   s->dist_fresh = false;  // (conservative: only a whole-grid reset re-arms the read-free x pass)
   CU(cudaStreamSynchronize(s->stream));
@@ -377,17 +388,23 @@ int gtop_sdf_set_occupancy_boxes(gtop_sdf* s, const int32_t* lo_hi, int64_t n) {
 int gtop_sdf_update_esdf(gtop_sdf* s) {
   REQUIRE(s, "null sdf");
   CU(cudaSetDevice(s->device));
-  if (!s->d1) {
+  if (!s->d1 || !s->d2) {
+    cudaFree(s->d1), cudaFree(s->d2);
+    s->d1 = s->d2 = nullptr;
     cudaError_t e = cudaMalloc(&s->d1, sizeof(int32_t) * s->nvox);
     if (e == cudaSuccess) e = cudaMalloc(&s->d2, sizeof(int32_t) * s->nvox);
-    if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("edt scratch: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      cudaFree(s->d1), cudaFree(s->d2);
+      s->d1 = s->d2 = nullptr;
+      return fail(GTOP_E_ALLOC, std::string("edt scratch: ") + cudaGetErrorString(e));
+    }
   }
   const int g[3] = {s->view.nx, s->view.ny, s->view.nz};
   const bool whole = s->win_lo[0] == 0 && s->win_lo[1] == 0 && s->win_lo[2] == 0 && s->win_hi[0] == g[0] - 1 &&
                      s->win_hi[1] == g[1] - 1 && s->win_hi[2] == g[2] - 1;
   if (whole) {
     CU(launch_edt(s->occ, s->d1, s->d2, s->dist, g[0], g[1], g[2], s->view.res, s->dist_fresh, s->stream, s->ev));
-    CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
+    if (s->quad) CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
     g_launches += 4;
   } else {  // the box setUpdateRange left (sdf_map.cpp:244-264)
     const VoxelBox b = window_box(s->win_lo, s->win_hi);
@@ -401,14 +418,17 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
       s->wcap = n;
     }
     CU(launch_edt_window(s->occ, s->wocc, s->d1, s->d2, s->wdist, s->dist, b, g[1], g[2], s->view.res, s->stream, s->ev));
-    CU(launch_build_quads_box(s->view, s->dist, s->quad, b, s->stream));
+    if (s->quad) CU(launch_build_quads_box(s->view, s->dist, s->quad, b, s->stream));
     g_launches += 6;
     for (int i = 0; i < 3; ++i) s->win_lo[i] = 0, s->win_hi[i] = g[i] - 1;  // :366-367
   }
   s->dist_fresh = false;
+  CU(cudaEventRecord(s->ev[4], s->stream));  // the map is ready for the evaluation kernels from here
   CU(cudaStreamSynchronize(s->stream));
   for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&s->last_ms[i], s->ev[i], s->ev[i + 1]);
   cudaEventElapsedTime(&s->last_ms[3], s->ev[0], s->ev[3]);
+  cudaEventElapsedTime(&s->last_ms[4], s->ev[3], s->ev[4]);
+  cudaEventElapsedTime(&s->last_ms[5], s->ev[0], s->ev[4]);
   return GTOP_OK;
 }
 
@@ -442,6 +462,19 @@ int gtop_sdf_last_edt_ms(const gtop_sdf* s, float ms[4]) {
   for (int i = 0; i < 4; ++i) ms[i] = s->last_ms[i];
   return GTOP_OK;
 }
+int gtop_sdf_last_update_ms(const gtop_sdf* s, float ms[6]) {
+  REQUIRE(s && ms, "null argument");
+  for (int i = 0; i < 6; ++i) ms[i] = s->last_ms[i];
+  return GTOP_OK;
+}
+int gtop_sdf_gather_layout(const gtop_sdf* s, int32_t* has_quad_copy, int64_t* resident_bytes) {
+  REQUIRE(s, "null sdf");
+  const int64_t quad = s->quad ? 32 * quad_elems(s->view.nx, s->view.ny, s->view.nz) : 0;
+  if (has_quad_copy) *has_quad_copy = s->quad ? 1 : 0;
+  // distances + occupancy + (EDT scratch once an update has run) + quad copy
+  if (resident_bytes) *resident_bytes = s->nvox * 9 + (s->d1 ? s->nvox * 8 : 0) + quad;
+  return GTOP_OK;
+}
 
 int gtop_sdf_download_distance(const gtop_sdf* s, double* host) {
   REQUIRE(s && host, "null argument");
@@ -454,7 +487,7 @@ int gtop_sdf_upload_distance(gtop_sdf* s, const double* host) {
   CU(cudaSetDevice(s->device));
   CU(cudaMemcpy(s->dist, host, sizeof(double) * s->nvox, cudaMemcpyHostToDevice));
   s->dist_fresh = false;
-  CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
+  if (s->quad) CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   ++g_launches;
   CU(cudaStreamSynchronize(s->stream));
   return GTOP_OK;
@@ -571,10 +604,19 @@ static int finish_handle(gtop_problems* p, cudaError_t e, gtop_problems** out) {
   return GTOP_OK;
 }
 
+// segment-count limit: the record layout (gtop_types.cuh) is indexed with 32-bit offsets
+static bool layout_fits(int m, int ns) { return m >= 2 && m <= 4096 && (int64_t)m * ns * 110 + (int64_t)m * 400 < ((int64_t)1 << 30); }
+
 static int check_params(const gtop_params* prm) {
   REQUIRE(prm, "null params");
   REQUIRE(prm->samples_per_segment >= 1 && prm->samples_per_segment <= 4096, "samples_per_segment out of range");
   REQUIRE(prm->r != 0.0, "r must be non-zero");
+  // the table exp2 of the kernels takes |y| < 2^26 with y = (d0 - d) log2(e) / r, |d| <= 10000 (unseen voxels)
+  REQUIRE((std::fabs(prm->d0) + 1.0e4) * 1.4427 / std::fabs(prm->r) < 3.0e7, "|d0| / r or 1e4 / r too large for the penalty's range");
+  if (prm->vel_acc_penalty)
+    REQUIRE(prm->r_v != 0.0 && prm->r_a != 0.0 && (std::fabs(prm->v0) + 1.0e3) * 1.4427 / std::fabs(prm->r_v) < 3.0e7 &&
+                (std::fabs(prm->a0) + 1.0e4) * 1.4427 / std::fabs(prm->r_a) < 3.0e7,
+            "r_v / r_a must be non-zero and v0 / r_v, a0 / r_a in the penalty's range with vel_acc_penalty");
   if (prm->vel_acc_penalty) REQUIRE(prm->r_v != 0.0 && prm->r_a != 0.0, "r_v and r_a must be non-zero with vel_acc_penalty");
   return GTOP_OK;
 }
@@ -582,6 +624,7 @@ static int check_params(const gtop_params* prm) {
 int gtop_problems_create_dense(int32_t np, int32_t m, const double* seg_time, const double* L, const double* R,
                                const double* Df, const gtop_params* prm, int device, gtop_problems** out) {
   REQUIRE(np >= 1 && m >= 2 && seg_time && L && R && Df && out, "bad argument");
+  REQUIRE(prm && layout_fits(m, prm->samples_per_segment), "segments x samples_per_segment out of range");
   if (int rc = check_params(prm)) return rc;
   REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
   CU(cudaSetDevice(device));
@@ -604,6 +647,7 @@ int gtop_problems_create_dense(int32_t np, int32_t m, const double* seg_time, co
 int gtop_problems_create_from_paths(int32_t np, int32_t m, const double* waypoints, const gtop_params* prm, int device,
                                     gtop_problems** out) {
   REQUIRE(np >= 1 && m >= 2 && waypoints && out, "bad argument");
+  REQUIRE(prm && layout_fits(m, prm->samples_per_segment), "segments x samples_per_segment out of range");
   if (int rc = check_params(prm)) return rc;
   REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
   CU(cudaSetDevice(device));
@@ -640,6 +684,7 @@ int gtop_problems_create_from_paths(int32_t np, int32_t m, const double* waypoin
 int gtop_problems_create_from_kino(int32_t np, int32_t m, const double* pos, const double* vel, const double* acc,
                                    const double* time, const gtop_params* prm, int device, gtop_problems** out) {
   REQUIRE(np >= 1 && m >= 2 && pos && vel && acc && time && out, "bad argument");
+  REQUIRE(prm && layout_fits(m, prm->samples_per_segment), "segments x samples_per_segment out of range");
   if (int rc = check_params(prm)) return rc;
   REQUIRE(gtop_device_count() > device && device >= 0, "no such CUDA device (this library has no CPU fallback)");
   CU(cudaSetDevice(device));
@@ -723,12 +768,14 @@ static int create_on_device(int32_t np, int32_t m, const double* pos, const doub
 int gtop_problems_create_from_paths_device(int32_t np, int32_t m, const double* waypoints, const gtop_params* prm,
                                            int device, gtop_problems** out) {
   REQUIRE(np >= 1 && m >= 2 && waypoints && out, "bad argument");
+  REQUIRE(prm && layout_fits(m, prm->samples_per_segment), "segments x samples_per_segment out of range");
   return create_on_device(np, m, waypoints, nullptr, nullptr, nullptr, prm, device, out);
 }
 
 int gtop_problems_create_from_kino_device(int32_t np, int32_t m, const double* pos, const double* vel, const double* acc,
                                           const double* time, const gtop_params* prm, int device, gtop_problems** out) {
   REQUIRE(np >= 1 && m >= 2 && pos && vel && acc && time && out, "bad argument");
+  REQUIRE(prm && layout_fits(m, prm->samples_per_segment), "segments x samples_per_segment out of range");
   return create_on_device(np, m, pos, vel, acc, time, prm, device, out);
 }
 
@@ -775,6 +822,11 @@ int gtop_problems_set_params(gtop_problems* p, const gtop_params* prm) {
   REQUIRE(p, "null problems");
   if (int rc = check_params(prm)) return rc;
   REQUIRE(prm->samples_per_segment == p->prm.samples_per_segment, "samples_per_segment is fixed at creation");
+  // baked into the device records, x0 and the NLopt box when the set was created: only the weights, the penalty
+  // constants, the solver settings and the velocity / acceleration flag can change on a live set
+  REQUIRE(prm->mean_v == p->prm.mean_v && prm->init_time == p->prm.init_time && prm->bos == p->prm.bos &&
+              prm->vos == p->prm.vos && prm->aos == p->prm.aos,
+          "mean_v, init_time, bos, vos, aos are fixed at creation: create a new problem set");
   p->prm = *prm;
   return GTOP_OK;
 }
@@ -855,17 +907,19 @@ int gtop_coeff_from_x(const gtop_problems* p, int32_t i, const double* x, double
 }
 
 // ================================================================================ evaluation
-static int check_eval(const gtop_sdf* sdf, const gtop_problems* pr, int64_t B, int64_t starts, int step) {
+static int check_eval(const gtop_sdf* sdf, const gtop_problems* pr, int64_t B, int64_t off, int64_t starts, int step) {
   REQUIRE(sdf && pr, "null handle");
   REQUIRE(sdf->device == pr->device, "sdf and problems live on different devices");
   REQUIRE(B >= 0 && starts >= 1, "bad batch shape");
+  REQUIRE(off >= 0, "traj_offset must be >= 0 (it selects the problem of every trajectory)");
+  REQUIRE(B <= (int64_t)1 << 40 && off <= (int64_t)1 << 60, "batch too large");
   REQUIRE(step >= 0 && step <= 2, "step must be 0, 1 or 2");
   return GTOP_OK;
 }
 
 int gtop_eval_batch_device(const gtop_sdf* sdf, const gtop_problems* pr, const double* X, int64_t B, int64_t off,
                            int64_t starts, int step, double* cost, double* grad, void* stream) {
-  if (int rc = check_eval(sdf, pr, B, starts, step)) return rc;
+  if (int rc = check_eval(sdf, pr, B, off, starts, step)) return rc;
   if (B == 0) return GTOP_OK;
   REQUIRE(X && cost && grad, "null device buffer");
   CU(cudaSetDevice(pr->device));
@@ -880,7 +934,7 @@ int gtop_eval_batch_device(const gtop_sdf* sdf, const gtop_problems* pr, const d
 int gtop_traj_metrics_device(const gtop_problems* pr, const double* X, int64_t B, int64_t off, int64_t starts,
                              double* metrics, void* stream) {
   REQUIRE(pr, "null problems");
-  REQUIRE(B >= 0 && starts >= 1, "bad batch shape");
+  REQUIRE(B >= 0 && starts >= 1 && off >= 0, "bad batch shape");
   if (B == 0) return GTOP_OK;
   REQUIRE(X && metrics, "null device buffer");
   CU(cudaSetDevice(pr->device));
@@ -915,7 +969,7 @@ int gtop_traj_metrics_host(const gtop_problems* pr, const double* X, int64_t B, 
 
 int gtop_eval_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, const double* X, int64_t B, int64_t off,
                          int64_t starts, int step, double* cost, double* grad, int64_t* n_oob) {
-  if (int rc = check_eval(sdf, cpr, B, starts, step)) return rc;
+  if (int rc = check_eval(sdf, cpr, B, off, starts, step)) return rc;
   if (n_oob) *n_oob = 0;
   if (B == 0) return GTOP_OK;
   REQUIRE(X && cost && grad, "null host buffer");
@@ -939,21 +993,26 @@ int gtop_eval_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, const do
   const int64_t nchunk = std::min<int64_t>(max_chunks, (B + 4095) / 4096);
   const int64_t per = ((B + nchunk - 1) / nchunk + 63) & ~int64_t(63);  // whole lane groups per chunk
   cudaStream_t s_k = pr->streams[0], s_in = pr->streams[1], s_out = pr->streams[2];
-  for (int64_t c = 0; c < nchunk; ++c) {
+  cudaError_t err = cudaSuccess;
+  auto ok = [&](cudaError_t e) { return err == cudaSuccess && (err = e) == cudaSuccess; };
+  for (int64_t c = 0; c < nchunk && err == cudaSuccess; ++c) {
     const int64_t b0 = c * per, bn = std::min(per, B - b0);
     if (bn <= 0) break;
-    CU(cudaMemcpyAsync(pr->dX + b0 * n, X + b0 * n, sizeof(double) * bn * n, cudaMemcpyHostToDevice, s_in));
-    CU(cudaEventRecord(pr->ev_in[c], s_in));
-    CU(cudaStreamWaitEvent(s_k, pr->ev_in[c], 0));
-    CU(launch_eval(sdf->view, pr->layout, pr->rec, pr->np, E, pr->dX + b0 * n, bn, off + b0, starts, pr->dcost + b0,
-                   pr->dgrad + b0 * n, pr->oob, 0, s_k));
+    ok(cudaMemcpyAsync(pr->dX + b0 * n, X + b0 * n, sizeof(double) * bn * n, cudaMemcpyHostToDevice, s_in)) &&
+        ok(cudaEventRecord(pr->ev_in[c], s_in)) && ok(cudaStreamWaitEvent(s_k, pr->ev_in[c], 0)) &&
+        ok(launch_eval(sdf->view, pr->layout, pr->rec, pr->np, E, pr->dX + b0 * n, bn, off + b0, starts, pr->dcost + b0,
+                       pr->dgrad + b0 * n, pr->oob, 0, s_k)) &&
+        ok(cudaEventRecord(pr->ev_done[c], s_k)) && ok(cudaStreamWaitEvent(s_out, pr->ev_done[c], 0)) &&
+        ok(cudaMemcpyAsync(grad + b0 * n, pr->dgrad + b0 * n, sizeof(double) * bn * n, cudaMemcpyDeviceToHost, s_out)) &&
+        ok(cudaMemcpyAsync(cost + b0, pr->dcost + b0, sizeof(double) * bn, cudaMemcpyDeviceToHost, s_out));
     ++g_launches;
-    CU(cudaEventRecord(pr->ev_done[c], s_k));
-    CU(cudaStreamWaitEvent(s_out, pr->ev_done[c], 0));
-    CU(cudaMemcpyAsync(grad + b0 * n, pr->dgrad + b0 * n, sizeof(double) * bn * n, cudaMemcpyDeviceToHost, s_out));
-    CU(cudaMemcpyAsync(cost + b0, pr->dcost + b0, sizeof(double) * bn, cudaMemcpyDeviceToHost, s_out));
   }
-  for (auto& st : pr->streams) CU(cudaStreamSynchronize(st));
+  // whatever happened, nothing may still be writing into the caller's buffers when this returns
+  for (auto& st : pr->streams) {
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (err == cudaSuccess) err = e;
+  }
+  CU(err);
   if (n_oob) return gtop_problems_take_out_of_map(pr, n_oob);
   return GTOP_OK;
 }
@@ -1020,7 +1079,7 @@ static int solve_workspace(gtop_problems* pr, int64_t B) {
 
 int gtop_solve_batch_device(const gtop_sdf* sdf, const gtop_problems* cpr, double* X, int64_t B, int64_t off,
                             int64_t starts, int step, int maxeval, double* minf, void* stream) {
-  if (int rc = check_eval(sdf, cpr, B, starts, step)) return rc;
+  if (int rc = check_eval(sdf, cpr, B, off, starts, step)) return rc;
   REQUIRE(maxeval >= 1, "maxeval must be >= 1");
   if (B == 0) return GTOP_OK;
   REQUIRE(X, "null device buffer");
@@ -1049,7 +1108,7 @@ int gtop_solve_batch_device(const gtop_sdf* sdf, const gtop_problems* cpr, doubl
 
 int gtop_solve_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, double* X, int64_t B, int64_t off, int64_t starts,
                           int step, int maxeval, double* minf) {
-  if (int rc = check_eval(sdf, cpr, B, starts, step)) return rc;
+  if (int rc = check_eval(sdf, cpr, B, off, starts, step)) return rc;
   if (B == 0) return GTOP_OK;
   REQUIRE(X, "null host buffer");
   gtop_problems* pr = const_cast<gtop_problems*>(cpr);
@@ -1073,7 +1132,7 @@ int gtop_solve_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, double*
 // ================================================================================ NLopt callback
 int gtop_objective_ctx_create(const gtop_sdf* sdf, const gtop_problems* pr, int32_t problem, int step,
                               gtop_objective_ctx** out) {
-  if (int rc = check_eval(sdf, pr, 1, 1, step)) return rc;
+  if (int rc = check_eval(sdf, pr, 1, 0, 1, step)) return rc;
   REQUIRE(out && problem >= 0 && problem < pr->np, "bad argument");
   CU(cudaSetDevice(pr->device));
   gtop_objective_ctx* c = new gtop_objective_ctx();

@@ -59,6 +59,10 @@ class GradTrajOptimizer {
 
   // ---- upstream API -------------------------------------------------------------------------------
   void initSDFMap(const Vec3& map_size_3d, const Vec3& origin, double resolution) {  // :112-115
+    // (the reference simply reassigns its SDFMap and may do so between solves: the callback context of the last solve
+    // holds the old map and goes with it)
+    gtop_objective_ctx_destroy(ctx_);
+    ctx_ = nullptr;
     gtop_sdf_destroy(sdf_);
     sdf_ = nullptr;
     const double o[3] = {origin.x, origin.y, origin.z}, s[3] = {map_size_3d.x, map_size_3d.y, map_size_3d.z};

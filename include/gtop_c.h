@@ -112,6 +112,13 @@ int gtop_sdf_set_occupancy_boxes(gtop_sdf* sdf, const int32_t* lo_hi, int64_t n)
 int gtop_sdf_update_esdf(gtop_sdf* sdf);
 /* device time of the last update_esdf: ms[0..2] = z/y/x pass kernels, ms[3] = total */
 int gtop_sdf_last_edt_ms(const gtop_sdf* sdf, float ms[4]);
+/* the same, through to "ready for the evaluation kernels": ms[0..2] = z/y/x passes, ms[3] = their sum, ms[4] = rebuild of
+ * the gather copy (0 for maps that keep none), ms[5] = start of the update to evaluator-ready */
+int gtop_sdf_last_update_ms(const gtop_sdf* sdf, float ms[6]);
+/* how the evaluation kernels read the field: has_quad_copy = 1 -> from the xy-quad copy (4x the field, two 256-bit loads
+ * per sample; maps whose copy stays under GTOP_QUAD_LIMIT_MB, default 1024), 0 -> straight from the distance field (big
+ * maps: eight 64-bit loads per sample, no copy to keep or rebuild).  resident_bytes = device memory the map holds. */
+int gtop_sdf_gather_layout(const gtop_sdf* sdf, int32_t* has_quad_copy, int64_t* resident_bytes);
 int gtop_sdf_download_distance(const gtop_sdf* sdf, double* host);
 int gtop_sdf_upload_distance(gtop_sdf* sdf, const double* host);
 int gtop_sdf_download_occupancy(const gtop_sdf* sdf, int32_t* host);

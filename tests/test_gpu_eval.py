@@ -321,3 +321,54 @@ def test_config5_batch_parity(gtop_lib):
         sl = slice(1024 * p, 1024 * (p + 1))
         cr, gr, oob_ref, _ = opt.eval_batch(X[sl], 2)
         assert rel_cost_err(c[sl], cr).max() <= TOL and rel_grad_err(g[sl], gr).max() <= TOL
+
+
+def test_plain_gather_equals_quad_gather(gtop_lib, monkeypatch):
+    """Maps too big for the xy-quad copy are gathered straight from the distance field (same corner values, same
+    clamping): identical results from every evaluation kernel, including the map border and out-of-map samples."""
+    api = _api()
+    cfg = fx.load_cfg("text_input")
+    om = oracle_map_from_cfg(cfg)
+    opt = oracle_problem(cfg, om, cfg["waypoints"])
+    X = _starts(opt, 64, seed=21)
+    X[5, 2 * opt.num_dp:2 * opt.num_dp + 9:3] += 4.0   # above the ceiling: out-of-map samples
+    X[6, 0:9:3] = -9.97                                # along the x = -10 face: border cells (idx = -1)
+    res = []
+    for limit in ("1024", "0"):
+        monkeypatch.setenv("GTOP_QUAD_LIMIT_MB", limit)
+        gm = _gpu_map_from_oracle(om)
+        assert gm.gather_layout()[0] == (limit != "0")
+        ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+        out = [ps.eval_host(gm, X, step=2, starts_per_problem=64),   # k_eval_mma
+               ps.eval_host(gm, X[:7], step=2, starts_per_problem=1)]  # k_eval_traj (ragged, 7 trajectories)
+        res.append(out)
+    for (c0, g0, o0), (c1, g1, o1) in zip(res[0], res[1]):
+        assert o0 == o1 and o0 > 0
+        assert np.array_equal(c0, c1) and np.array_equal(g0, g1)
+    c_ref, g_ref, _, _ = opt.eval_batch(X, 2)
+    assert rel_cost_err(res[1][0][0], c_ref).max() <= TOL and rel_grad_err(res[1][0][1], g_ref).max() <= TOL
+
+
+def test_argument_checks_of_the_evaluation_entry_points(gtop_lib):
+    """A negative traj_offset would index problems out of bounds; fields baked into the records at creation cannot be
+    changed on a live set; penalty constants outside the kernels' exponent range are refused."""
+    from grad_traj_optimization_b200._capi import GtopError
+    api = _api()
+    cfg = fx.load_cfg("opti_node")
+    om = oracle_map_from_cfg(cfg)
+    gm = _gpu_map_from_oracle(om)
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+    X = ps.x0()
+    with pytest.raises(GtopError, match="traj_offset"):
+        ps.eval_host(gm, X, traj_offset=-1)
+    with pytest.raises(GtopError, match="fixed at creation"):
+        ps.set_params(api.make_params(dict(cfg["params"], bos=1.0)))
+    ps.set_params(api.make_params(dict(cfg["params"], wc=2.5)))  # weights may change
+    c0, _, _ = ps.eval_host(gm, X)
+    ps.set_params(api.make_params(cfg["params"]))
+    c1, _, _ = ps.eval_host(gm, X)
+    assert c0[0] != c1[0]
+    with pytest.raises(GtopError, match="range"):
+        api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(dict(cfg["params"], r=1e-5)))
+    t = gm.last_update_ms()
+    assert len(t) == 6
