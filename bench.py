@@ -296,6 +296,7 @@ def run_ours(args):
     X, traj_offset = Xfull[lo:lo + per_gpu], lo
     B, n = X.shape
     timer = DeviceTimer(torch, api, gm, ps, X, starts, traj_offset)
+    head_nbuf, head_ws = timer.nbuf, timer.working_set_mb()
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -358,11 +359,10 @@ def run_ours(args):
     if args.scaling == "strong" and world > 1:
         del timer
         torch.cuda.empty_cache()
-        wt = DeviceTimer(torch, api, gm, ps, Xfull, starts, 0)
-        wms, _ = wt.run(max(5, min(args.steps, 40)), 3, barrier)
+        timer = DeviceTimer(torch, api, gm, ps, Xfull, starts, 0)
+        wms, _ = timer.run(max(5, min(args.steps, 40)), 3, barrier)
         (wms,) = max_over_ranks(wms)
         weak = {"per_gpu_batch": full, "global_batch": full * n_gpus, "ms_per_step": wms, "value": full * n_gpus / (wms * 1e-3)}
-        timer = wt
 
     # ---- FP64 ceilings measured in this run ------------------------------------------------
     fp64 = None
@@ -377,6 +377,8 @@ def run_ours(args):
 
     ms_step, e2e_ms = max_over_ranks(ms_step, e2e_ms)
     sampler.stop_flag = True
+    l2_note = ("%d rotating X/grad/cost buffer sets per GPU (%.0f MB > 126 MB L2); the 16 MB SDF grid is L2-resident by "
+               "construction" % (head_nbuf, head_ws))
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
@@ -388,7 +390,7 @@ def run_ours(args):
         configs = edt = None
         if world == 1 and not args.no_configs:
             try:
-                del timer
+                timer = None
                 torch.cuda.empty_cache()
                 configs, edt = other_shapes(torch, api, fx, gm, peak, min(args.steps, 100))
             except Exception as exc:
@@ -408,8 +410,7 @@ def run_ours(args):
                        "samples_per_segment": N_SAMP,
                        "parallelism": "batch %s across %d GPU(s) in contiguous blocks, SDF replicated, no collective" % (
                            "sharded" if args.scaling == "strong" else "replicated per GPU (weak)", n_gpus),
-                       "l2": "%d rotating X/grad/cost buffer sets per GPU (%.0f MB > 126 MB L2); the 16 MB SDF grid is "
-                             "L2-resident by construction" % (timer.nbuf, timer.working_set_mb()),
+                       "l2": l2_note,
                        "out_of_map_samples_per_step": oob // max(1, args.steps + max(args.warmup, 3))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": "k_eval_mma",

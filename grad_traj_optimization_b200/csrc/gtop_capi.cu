@@ -989,7 +989,7 @@ int gtop_eval_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, const do
   // chunked pipeline over three streams: all H2D copies of x back to back on the copy-in stream, the kernels
   // on the compute stream as their chunk lands, cost/gradient copied out on the copy-out stream as each
   // kernel finishes (the two PCIe directions and the SMs are busy at the same time)
-  static const int64_t max_chunks = [] { const char* e = std::getenv("GTOP_HOST_CHUNKS"); return e ? std::max(1L, std::min(16L, std::atol(e))) : 8L; }();
+  static const int64_t max_chunks = [] { const char* e = std::getenv("GTOP_HOST_CHUNKS"); return e ? std::max(1L, std::min(16L, std::atol(e))) : 16L; }();
   const int64_t nchunk = std::min<int64_t>(max_chunks, (B + 4095) / 4096);
   const int64_t per = ((B + nchunk - 1) / nchunk + 63) & ~int64_t(63);  // whole lane groups per chunk
   cudaStream_t s_k = pr->streams[0], s_in = pr->streams[1], s_out = pr->streams[2];

@@ -372,3 +372,38 @@ def test_argument_checks_of_the_evaluation_entry_points(gtop_lib):
         api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(dict(cfg["params"], r=1e-5)))
     t = gm.last_update_ms()
     assert len(t) == 6
+
+
+@pytest.mark.parametrize("vel_acc", [0, 1])
+def test_segment_parallel_general_kernel_is_bit_identical(gtop_lib, vel_acc):
+    """Small general batches run k_eval_traj_seg (one warp per segment), large ones k_eval_traj (a quarter-warp walks
+    the segments): same per-segment code, two-term row sums, cost folded in segment order -> the same bits, so that the
+    choice by batch size never shows in the results; both against the oracle."""
+    api = _api()
+    om, dist = map_a_oracle()
+    gm = _gpu_map_from_oracle(om)
+    m, nprob, B = 6, 512, 18000
+    wps = np.stack([fx.random_waypoints(p, m, dist, fx.MAP_A["map_origin"], fx.MAP_A["resolution"]) for p in range(nprob)])
+    prm = dict(fx.PARAMS_OPTI, vel_acc_penalty=vel_acc, alpha_v=2.0, alpha_a=1.5)
+    ps = api.ProblemSet.from_paths(wps, api.make_params(prm), setup="device")
+    x0, (lb, ub) = ps.x0(), ps.bounds()
+    rng = np.random.default_rng(5)
+    pid = np.arange(B) % nprob
+    X = np.clip(x0[pid] + rng.normal(0.0, 0.3, (B, ps.n)), lb[pid], ub[pid])
+    c, g, _ = ps.eval_host(gm, X, step=2, starts_per_problem=1)        # chunks of 4,096 < 16,384: segment-parallel
+    ps.take_out_of_map()
+    import torch
+    Xd = torch.from_numpy(X).cuda()
+    cd, gd = torch.empty(B, dtype=torch.float64, device="cuda"), torch.empty_like(Xd)
+    ps.eval_device(gm, Xd, cd, gd, step=2, starts_per_problem=1)      # one launch of 18,000: the sequential kernel
+    torch.cuda.synchronize()
+    assert np.array_equal(cd.cpu().numpy(), c) and np.array_equal(gd.cpu().numpy(), g)
+    for lo, hi in ((0, 1), (5000, 5777), (17990, 18000)):             # ragged slices, offsets that are not multiples of 4
+        cs, gs, _ = ps.eval_host(gm, X[lo:hi], step=2, starts_per_problem=1, traj_offset=lo)
+        assert np.array_equal(cs, c[lo:hi]) and np.array_equal(gs, g[lo:hi])
+    from common import oracle_params
+    for p in (0, 7, 511):
+        opt = oracle_problem(prm, om, wps[p])
+        rows = np.nonzero(pid == p)[0][:4]
+        cr, gr, _, _ = opt.eval_batch(X[rows], 2)
+        assert rel_cost_err(c[rows], cr).max() <= TOL and rel_grad_err(g[rows], gr).max() <= TOL
