@@ -78,13 +78,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+// x and the gradient stream through once: evict-first in L2, so that they do not push out the map and the per-problem
+// tables, which every launch re-reads
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_load_stream(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(l2_evict_first_policy())
+               : "memory");
+}
 __device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes), "l"(l2_evict_first_policy())
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -242,7 +256,7 @@ k_eval_mma(SdfView S, ProbLayout PL, PairSmem sm, const double* __restrict__ pro
   if (whole) {
     if (tid == 0) {
       mbar_expect_tx(mbar, xbytes + 144u);
-      bulk_load(xin, X + b0 * n, xbytes, mbar);
+      bulk_load_stream(xin, X + b0 * n, xbytes, mbar);
       bulk_load(xin + 8 * n, pr + PL.off_Df, 144u, mbar);
     }
   } else {
