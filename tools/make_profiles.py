@@ -39,7 +39,7 @@ def main():
         seq.append((name, v))
     total = sum(a[1] for a in agg.values())
     with open(os.path.join(out_dir, "%s_launches.md" % tag), "w") as f:
-        f.write("# %s — ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu-baseline`\n\n" % tag)
+        f.write("# %s — ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs`\n\n" % tag)
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised launches: the SHARE "
                 "of each kernel is meaningful, not the absolute time).  %d launches, %.1f us total.\n\n" % (len(seq), total))
         f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
