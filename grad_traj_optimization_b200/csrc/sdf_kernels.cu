@@ -348,8 +348,9 @@ __device__ __forceinline__ double sqrt_small_int(int v) {
 }
 // res * sqrt(val) as the reference computes it (sdf_map.cpp:356-360), bit for bit
 __device__ __forceinline__ double edt_distance(double res, int val) {
-  if (val == 0) return 0.0 * res;
-  return res * ((val <= kFastSqrtMax) ? sqrt_small_int(val) : sqrt((double)val));
+  if (val > kFastSqrtMax) return res * sqrt((double)val);  // (rows longer than 8192 voxels only)
+  const double r = sqrt_small_int(max(val, 1));            // occupied voxel: sqrt(0) = 0 without the seed's infinity
+  return res * (val == 0 ? 0.0 : r);
 }
 
 // exhaustive check of sqrt_small_int against the IEEE square root: counts the integers in [1, vmax] where they differ
@@ -390,15 +391,20 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
   // loads are in flight while the envelope logic runs.
   constexpr int kPF = 8;
   int gbuf[kPF];
+  const int32_t* __restrict__ gp = g;  // element u0 + kPF + k of the row is gp[0] when it is fetched (running pointer:
+                                       // a 64-bit multiply per element was 10 % of the pass)
 #pragma unroll
-  for (int k = 0; k < kPF; ++k) gbuf[k] = (k < n) ? g[(int64_t)k * gstride] : kInf;
+  for (int k = 0; k < kPF; ++k) {
+    gbuf[k] = (k < n) ? *gp : kInf;
+    gp += gstride;
+  }
   for (int u0 = 0; u0 < n; u0 += kPF) {
     int gcur[kPF];
 #pragma unroll
     for (int k = 0; k < kPF; ++k) {
       gcur[k] = gbuf[k];
-      const int un = u0 + kPF + k;
-      gbuf[k] = (un < n) ? g[(int64_t)un * gstride] : kInf;
+      gbuf[k] = (u0 + kPF + k < n) ? *gp : kInf;
+      gp += gstride;
     }
 #pragma unroll
     for (int k = 0; k < kPF; ++k) {
@@ -442,6 +448,8 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
     }
     return;
   }
+  double* od = FINAL ? out_d + (int64_t)(n - 1) * gstride : nullptr;
+  int32_t* oi = FINAL ? nullptr : out_i + (int64_t)(n - 1) * gstride;
   for (int u = n - 1; u >= 0; --u) {
     while (tp != kNoSite && tt > u) {
       ts = tp;
@@ -451,12 +459,13 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
     const int d = u - ts;
     const int val = d * d + tg;
     if (FINAL) {
-      double* o = out_d + (int64_t)u * gstride;
       // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360); after resetBuffer old is 10000 everywhere,
       // so the read of the old value is skipped
-      *o = fmin(edt_distance(res, val), fresh ? 10000.0 : *o);
+      *od = fmin(edt_distance(res, val), fresh ? 10000.0 : *od);
+      od -= gstride;
     } else {
-      out_i[(int64_t)u * gstride] = val;
+      *oi = val;
+      oi -= gstride;
     }
   }
 }

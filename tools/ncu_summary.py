@@ -10,8 +10,12 @@ import io
 import subprocess
 
 
+KERNEL = None  # --kernel regex: restrict both pages to one kernel of a multi-kernel report
+
+
 def ncu_csv(rep, page):
-    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", page, "--csv"] + (["-k", "regex:" + KERNEL] if KERNEL else [])
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
@@ -37,8 +41,11 @@ def main():
     ap.add_argument("rep")
     ap.add_argument("--units", type=float, default=655360.0, help="work units per launch (e.g. trajectory-segments)")
     ap.add_argument("--kernel-index", type=int, default=0)
+    ap.add_argument("--kernel", default=None, help="regex: pick this kernel of a multi-kernel report")
     ap.add_argument("--hot", type=int, default=0, help="print the N SASS instructions with most stall samples")
     args = ap.parse_args()
+    global KERNEL
+    KERNEL = args.kernel
 
     raw = ncu_csv(args.rep, "raw")
     hdr, units, data = raw[0], raw[1], raw[2:]
