@@ -134,8 +134,8 @@ struct SdfCell {
 };
 
 // kPlain: the map keeps no quad copy (maps too big for one: the copy is 4x the field and has to be rebuilt after every
-// update): the eight corners come straight from `dist`, z fastest — eight 64-bit loads from four 32-byte sectors where
-// the quad copy needs two 256-bit loads from two; same values, same clamping.
+// update): the eight corners come straight from `dist`, which such maps keep in 8 x 8 x 4 bricks (DistLayout) — eight
+// 64-bit loads where the quad copy needs two 256-bit loads; same values, same clamping.
 template <bool kNoAlloc, bool kPlain = false>
 __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double py, double pz, float fx32, float fy32,
                                            float fz32, SdfCell& c) {
@@ -165,13 +165,16 @@ __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double p
   const int x0 = max(min(ix, S.nx - 1), 0), y0 = max(min(iy, S.ny - 1), 0);
   const int z0 = max(min(iz, S.nz - 1), 0), z1 = max(min(iz + 1, S.nz - 1), 0);
   if (kPlain) {
-    const int x1 = min(x0 + 1, S.nx - 1), y1 = min(y0 + 1, S.ny - 1), dz = z1 - z0;
-    const double* __restrict__ r00 = S.dist + ((size_t)x0 * S.ny + y0) * S.nz + z0;
-    const double* __restrict__ r01 = S.dist + ((size_t)x0 * S.ny + y1) * S.nz + z0;
-    const double* __restrict__ r10 = S.dist + ((size_t)x1 * S.ny + y0) * S.nz + z0;
-    const double* __restrict__ r11 = S.dist + ((size_t)x1 * S.ny + y1) * S.nz + z0;
-    c.q0.v00 = __ldg(r00), c.q0.v01 = __ldg(r01), c.q0.v10 = __ldg(r10), c.q0.v11 = __ldg(r11);
-    c.q1.v00 = __ldg(r00 + dz), c.q1.v01 = __ldg(r01 + dz), c.q1.v10 = __ldg(r10 + dz), c.q1.v11 = __ldg(r11 + dz);
+    const int x1 = min(x0 + 1, S.nx - 1), y1 = min(y0 + 1, S.ny - 1);
+    // brick address = column part (x,y) + height part (z): [x>>3][y>>3][z>>2][x&7][y&7][z&3]
+    const int bx0 = (x0 >> 3) * S.lay.nby, bx1 = (x1 >> 3) * S.lay.nby;
+    const int ox0 = (x0 & 7) << 5, ox1 = (x1 & 7) << 5, oy0 = (y0 & 7) << 2, oy1 = (y1 & 7) << 2;
+    const size_t c00 = ((size_t)(bx0 + (y0 >> 3)) * S.lay.nbz << 8) + (ox0 | oy0), c01 = ((size_t)(bx0 + (y1 >> 3)) * S.lay.nbz << 8) + (ox0 | oy1);
+    const size_t c10 = ((size_t)(bx1 + (y0 >> 3)) * S.lay.nbz << 8) + (ox1 | oy0), c11 = ((size_t)(bx1 + (y1 >> 3)) * S.lay.nbz << 8) + (ox1 | oy1);
+    const int h0 = ((z0 >> 2) << 8) | (z0 & 3), h1 = ((z1 >> 2) << 8) | (z1 & 3);
+    const double* __restrict__ D = S.dist;
+    c.q0.v00 = __ldg(D + c00 + h0), c.q0.v01 = __ldg(D + c01 + h0), c.q0.v10 = __ldg(D + c10 + h0), c.q0.v11 = __ldg(D + c11 + h0);
+    c.q1.v00 = __ldg(D + c00 + h1), c.q1.v01 = __ldg(D + c01 + h1), c.q1.v10 = __ldg(D + c10 + h1), c.q1.v11 = __ldg(D + c11 + h1);
     return;
   }
   const int e0 = ((((x0 >> 1) * S.nyh + (y0 >> 1)) * S.nz + z0) << 2) + ((x0 & 1) << 1) + (y0 & 1);

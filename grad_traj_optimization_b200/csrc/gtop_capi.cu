@@ -23,15 +23,16 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
                         const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
                         int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
                         int max_ctas, cudaStream_t stream);
-cudaError_t launch_fill(double* dist, uint8_t* occ, int64_t n, double dval, cudaStream_t st);
+cudaError_t launch_fill(double* dist, int64_t ndist, uint8_t* occ, int64_t n, double dval, cudaStream_t st);
+cudaError_t launch_relayout(const double* src, double* dst, const DistLayout& lay, int nx, bool to_linear, cudaStream_t st);
 cudaError_t launch_build_quads(const SdfView& S, const double* dist, void* quad, cudaStream_t st);
 cudaError_t launch_set_occupancy(const SdfView& S, uint8_t* occ, const double* pts_dev, int64_t n, cudaStream_t st);
 cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t* boxes_dev, int64_t n,
                              cudaStream_t st);
 cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
-                       bool fresh, cudaStream_t st, cudaEvent_t* ev);
+                       bool fresh, cudaStream_t st, cudaEvent_t* ev, const DistLayout* lay);
 cudaError_t launch_edt_window(const uint8_t* occ, uint8_t* wocc, int32_t* d1, int32_t* d2, double* wdist, double* dist,
-                              const VoxelBox& b, int ny, int nz, double res, cudaStream_t st, cudaEvent_t* ev);
+                              const VoxelBox& b, const DistLayout& lay, double res, cudaStream_t st, cudaEvent_t* ev);
 cudaError_t launch_build_quads_box(const SdfView& S, const double* dist, void* quad, const VoxelBox& b, cudaStream_t st);
 cudaError_t launch_setup_problems(const ProbLayout& PL, double mean_v, double init_time, const double* pos_dev,
                                   const double* time_dev, int np, double* rec_dev, int* status_dev, cudaStream_t st);
@@ -39,7 +40,7 @@ cudaError_t launch_traj_metrics(const ProbLayout& PL, const double* prob, int nu
                                 int64_t traj_offset, int64_t starts_per_problem, double* out, cudaStream_t st);
 cudaError_t launch_query_dynamic(const SdfView& S, const double* boxes_dev, int nbox, double time, const double* pos_dev,
                                  int64_t n, double* dist_dev, double* grad_dev, double* coarse_dev, cudaStream_t st);
-cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, int ny, int nz, double dval, cudaStream_t st);
+cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, const DistLayout& lay, double dval, cudaStream_t st);
 cudaError_t measure_fp64_peak(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev, cudaStream_t st);
 bool eval_one_applicable(const ProbLayout& PL);
@@ -96,6 +97,7 @@ struct gtop_sdf {
   SdfView view{};
   double origin[3], map_size[3];
   int64_t nvox = 0;
+  int64_t ndist = 0;  // doubles in `dist` (brick-padded for maps without a quad copy)
   double* dist = nullptr;
   void* quad = nullptr;  // xy-quad copy of dist (SdfView::quad), rebuilt whenever dist changes; nullptr for big maps
   uint8_t* occ = nullptr;
@@ -245,7 +247,6 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
   }
   s->nvox = (int64_t)g[0] * g[1] * g[2];
   for (int i = 0; i < 3; ++i) s->win_lo[i] = 0, s->win_hi[i] = g[i] - 1;
-  cudaError_t e = cudaMalloc(&s->dist, sizeof(double) * s->nvox);
   // The xy-quad copy (4x the field) halves the L1 wavefronts of a gather and pays while it stays cache-resident; a map
   // whose copy would not (default: above 1 GiB) is gathered straight from `dist`: no 4x footprint, and no rebuild of the
   // copy — more bytes than the whole EDT moves — between an update and the first evaluation.
@@ -253,6 +254,10 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
   const double quad_limit_mb = qenv ? std::atof(qenv) : 1024.0;
   const size_t quad_bytes = 32 * (size_t)quad_elems(g[0], g[1], g[2]);
   const bool with_quad = (double)quad_bytes <= quad_limit_mb * 1048576.0;
+  // ... and keeps the field itself in 8 x 8 x 4 bricks (DistLayout) instead of the reference's linear order
+  v.lay.ny = g[1], v.lay.nz = g[2], v.lay.nby = (g[1] + 7) / 8, v.lay.nbz = (g[2] + 3) / 4, v.lay.bricks = with_quad ? 0 : 1;
+  s->ndist = dist_elems(g[0], g[1], g[2], !with_quad);
+  cudaError_t e = cudaMalloc(&s->dist, sizeof(double) * s->ndist);
   if (e == cudaSuccess && with_quad) e = cudaMalloc(&s->quad, quad_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&s->occ, s->nvox);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -263,7 +268,7 @@ int gtop_sdf_create(const double origin[3], double resolution, const double map_
   }
   v.dist = s->dist;
   v.quad = s->quad;
-  e = launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream);  // sdf_map.cpp:22-23
+  e = launch_fill(s->dist, s->ndist, s->occ, s->nvox, 10000.0, s->stream);  // sdf_map.cpp:22-23
   s->dist_fresh = true;
   if (e == cudaSuccess && s->quad) e = launch_build_quads(v, s->dist, s->quad, s->stream);
   g_launches += 2;
@@ -297,7 +302,7 @@ int gtop_sdf_grid(const gtop_sdf* s, int32_t grid[3]) {
 int gtop_sdf_reset(gtop_sdf* s) {
   REQUIRE(s, "null sdf");
   CU(cudaSetDevice(s->device));
-  CU(launch_fill(s->dist, s->occ, s->nvox, 10000.0, s->stream));
+  CU(launch_fill(s->dist, s->ndist, s->occ, s->nvox, 10000.0, s->stream));
   s->dist_fresh = true;
   if (s->quad) CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   g_launches += 2;
@@ -332,7 +337,7 @@ int gtop_sdf_reset_range(gtop_sdf* s, const double min_pos[3], const double max_
     return fail(GTOP_E_INVALID, "reset range: empty box or box outside the map");
   CU(cudaSetDevice(s->device));
   const VoxelBox b = window_box(lo, hi);
-  CU(launch_box_reset(s->dist, s->occ, b, s->view.ny, s->view.nz, 10000.0, s->stream));  // sdf_map.cpp:45-52
+  CU(launch_box_reset(s->dist, s->occ, b, s->view.lay, 10000.0, s->stream));  // sdf_map.cpp:45-52
   if (s->quad) CU(launch_build_quads_box(s->view, s->dist, s->quad, b, s->stream));
   g_launches += 2;
   s->dist_fresh = false;  // (conservative: only a whole-grid reset re-arms the read-free x pass)
@@ -403,7 +408,7 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
   const bool whole = s->win_lo[0] == 0 && s->win_lo[1] == 0 && s->win_lo[2] == 0 && s->win_hi[0] == g[0] - 1 &&
                      s->win_hi[1] == g[1] - 1 && s->win_hi[2] == g[2] - 1;
   if (whole) {
-    CU(launch_edt(s->occ, s->d1, s->d2, s->dist, g[0], g[1], g[2], s->view.res, s->dist_fresh, s->stream, s->ev));
+    CU(launch_edt(s->occ, s->d1, s->d2, s->dist, g[0], g[1], g[2], s->view.res, s->dist_fresh, s->stream, s->ev, &s->view.lay));
     if (s->quad) CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
     g_launches += 4;
   } else {  // the box setUpdateRange left (sdf_map.cpp:244-264)
@@ -417,7 +422,7 @@ int gtop_sdf_update_esdf(gtop_sdf* s) {
       if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("edt window scratch: ") + cudaGetErrorString(e));
       s->wcap = n;
     }
-    CU(launch_edt_window(s->occ, s->wocc, s->d1, s->d2, s->wdist, s->dist, b, g[1], g[2], s->view.res, s->stream, s->ev));
+    CU(launch_edt_window(s->occ, s->wocc, s->d1, s->d2, s->wdist, s->dist, b, s->view.lay, s->view.res, s->stream, s->ev));
     if (s->quad) CU(launch_build_quads_box(s->view, s->dist, s->quad, b, s->stream));
     g_launches += 6;
     for (int i = 0; i < 3; ++i) s->win_lo[i] = 0, s->win_hi[i] = g[i] - 1;  // :366-367
@@ -472,20 +477,43 @@ int gtop_sdf_gather_layout(const gtop_sdf* s, int32_t* has_quad_copy, int64_t* r
   const int64_t quad = s->quad ? 32 * quad_elems(s->view.nx, s->view.ny, s->view.nz) : 0;
   if (has_quad_copy) *has_quad_copy = s->quad ? 1 : 0;
   // distances + occupancy + (EDT scratch once an update has run) + quad copy
-  if (resident_bytes) *resident_bytes = s->nvox * 9 + (s->d1 ? s->nvox * 8 : 0) + quad;
+  if (resident_bytes) *resident_bytes = s->ndist * 8 + s->nvox + (s->d1 ? s->nvox * 8 : 0) + quad;
   return GTOP_OK;
 }
 
 int gtop_sdf_download_distance(const gtop_sdf* s, double* host) {
   REQUIRE(s && host, "null argument");
   CU(cudaSetDevice(s->device));
-  CU(cudaMemcpy(host, s->dist, sizeof(double) * s->nvox, cudaMemcpyDeviceToHost));
+  if (!s->view.lay.bricks) {
+    CU(cudaMemcpy(host, s->dist, sizeof(double) * s->nvox, cudaMemcpyDeviceToHost));
+    return GTOP_OK;
+  }
+  // bricks -> the reference's linear order through a device staging buffer
+  double* tmp = nullptr;
+  CU(cudaMalloc(&tmp, sizeof(double) * s->nvox));
+  cudaError_t e = launch_relayout(s->dist, tmp, s->view.lay, s->view.nx, true, s->stream);
+  ++g_launches;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host, tmp, sizeof(double) * s->nvox, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(tmp);
+  CU(e);
   return GTOP_OK;
 }
 int gtop_sdf_upload_distance(gtop_sdf* s, const double* host) {
   REQUIRE(s && host, "null argument");
   CU(cudaSetDevice(s->device));
-  CU(cudaMemcpy(s->dist, host, sizeof(double) * s->nvox, cudaMemcpyHostToDevice));
+  if (!s->view.lay.bricks) {
+    CU(cudaMemcpy(s->dist, host, sizeof(double) * s->nvox, cudaMemcpyHostToDevice));
+  } else {
+    double* tmp = nullptr;
+    CU(cudaMalloc(&tmp, sizeof(double) * s->nvox));
+    cudaError_t e = cudaMemcpyAsync(tmp, host, sizeof(double) * s->nvox, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = launch_relayout(tmp, s->dist, s->view.lay, s->view.nx, false, s->stream);
+    ++g_launches;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(tmp);
+    CU(e);
+  }
   s->dist_fresh = false;
   if (s->quad) CU(launch_build_quads(s->view, s->dist, s->quad, s->stream));
   ++g_launches;
@@ -510,6 +538,7 @@ int gtop_sdf_upload_occupancy(gtop_sdf* s, const int32_t* host) {
 }
 int gtop_sdf_distance_device_ptr(const gtop_sdf* s, const double** p) {
   REQUIRE(s && p, "null argument");
+  REQUIRE(!s->view.lay.bricks, "the map keeps its field in 8x8x4 bricks (no quad copy): use gtop_sdf_download_distance");
   *p = s->dist;
   return GTOP_OK;
 }

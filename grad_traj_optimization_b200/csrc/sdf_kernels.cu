@@ -31,12 +31,23 @@ namespace gtop {
 static constexpr int kInf = 0x3fffffff;  // "no occupied voxel" marker for int32 squared distances
 
 // ---------------------------------------------------------------------------------------------
-__global__ void k_fill(double* __restrict__ dist, uint8_t* __restrict__ occ, int64_t n, double dval) {
+__global__ void k_fill(double* __restrict__ dist, int64_t ndist, uint8_t* __restrict__ occ, int64_t n, double dval) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    dist[i] = dval;
-    occ[i] = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ndist; i += stride) {
+    dist[i] = dval;  // (brick padding included: never read)
+    if (i < n) occ[i] = 0;
   }
+}
+// distance field between the linear order (host side, reference order) and the map's own layout
+__global__ void k_relayout(const double* __restrict__ src, double* __restrict__ dst, DistLayout lay, int nx, bool to_linear) {
+  const int64_t n = (int64_t)nx * lay.ny * lay.nz;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int z = (int)(i % lay.nz);
+  const int64_t c = i / lay.nz;
+  const int64_t a = lay.at((int)(c / lay.ny), (int)(c % lay.ny), z);
+  if (to_linear) dst[i] = src[a];
+  else dst[a] = src[i];
 }
 
 // xy-quad copy of the distance field for the evaluation kernels' 256-bit gathers (see SdfView::quad).
@@ -103,13 +114,18 @@ __device__ __forceinline__ int64_t box_voxel(const VoxelBox& b, int ny, int nz, 
   return ((int64_t)(b.x0 + x) * ny + (b.y0 + y)) * nz + (b.z0 + z);
 }
 // SDFMap::resetBuffer(min_pos, max_pos) (sdf_map.cpp:28-53): occupancy 0, distance 10000 inside the box
-__global__ void k_box_reset(double* __restrict__ dist, uint8_t* __restrict__ occ, VoxelBox b, int ny, int nz, double dval,
+// the same voxel in the distance field's own layout
+__device__ __forceinline__ int64_t box_voxel_dist(const VoxelBox& b, const DistLayout& lay, int64_t i) {
+  const int z = (int)(i % b.wz);
+  const int64_t c = i / b.wz;
+  return lay.at(b.x0 + (int)(c / b.wy), b.y0 + (int)(c % b.wy), b.z0 + z);
+}
+__global__ void k_box_reset(double* __restrict__ dist, uint8_t* __restrict__ occ, VoxelBox b, DistLayout lay, double dval,
                             int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t a = box_voxel(b, ny, nz, i);
-  dist[a] = dval;
-  occ[a] = 0;
+  dist[box_voxel_dist(b, lay, i)] = dval;
+  occ[box_voxel(b, lay.ny, lay.nz, i)] = 0;
 }
 __global__ void k_box_gather_occ(const uint8_t* __restrict__ occ, uint8_t* __restrict__ wocc, VoxelBox b, int ny, int nz,
                                  int64_t n) {
@@ -117,11 +133,11 @@ __global__ void k_box_gather_occ(const uint8_t* __restrict__ occ, uint8_t* __res
   if (i < n) wocc[i] = occ[box_voxel(b, ny, nz, i)];
 }
 // min(resolution*sqrt(val), old) (sdf_map.cpp:356-360) for the voxels of the box
-__global__ void k_box_merge(const double* __restrict__ wdist, double* __restrict__ dist, VoxelBox b, int ny, int nz,
+__global__ void k_box_merge(const double* __restrict__ wdist, double* __restrict__ dist, VoxelBox b, DistLayout lay,
                             int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t a = box_voxel(b, ny, nz, i);
+  const int64_t a = box_voxel_dist(b, lay, i);
   dist[a] = fmin(wdist[i], dist[a]);
 }
 
@@ -376,10 +392,12 @@ cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev
 // map moved 184 GB through L1/L2 for 19 GB of useful traffic.)  F(x,i) = (x-i)^2 + g(i).
 // Rows up to 8192 long keep every intermediate below 2^31 (u^2 + 3 n^2 <= 2.7e8), so the intersection
 // is a 32-bit division; longer rows use 64-bit arithmetic.
-template <int MAXN, bool FINAL>
+// Output: out_i (int32, same stride as the input) or, FINAL, the fp64 distances: out_d points at the row's LAST element
+// and walks down by gstride (linear field) or, BRICK, by 32 doubles inside an 8-voxel x-brick and `ojump` across bricks.
+template <int MAXN, bool FINAL, bool BRICK = false>
 __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int64_t gstride, int n,
                                              int32_t* __restrict__ out_i, double* __restrict__ out_d, double res,
-                                             bool fresh) {
+                                             bool fresh, int64_t ojump = 0) {
   typedef typename std::conditional<(MAXN <= 8192), int, long long>::type wide_t;
   // Hull sites as a linked list embedded in a per-site array: st[u] = (start_u | prev_u << 16, g(u)) is written when
   // site u is pushed — every lane of a warp is at the same u, so the store is coalesced (a compacted stack indexed by
@@ -439,16 +457,18 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
     }
   }
   if (ts == kNoSite) {  // whole row infinite: res*sqrt(DBL_MAX) upstream, never below the old value (<= 10000)
-    for (int u = 0; u < n; ++u) {
+    double* od = out_d;
+    for (int u = n - 1; u >= 0; --u) {
       if (FINAL) {
-        if (fresh) out_d[(int64_t)u * gstride] = 10000.0;
+        if (fresh) *od = 10000.0;
+        od -= BRICK ? ((u & 7) ? (int64_t)32 : ojump) : gstride;
       } else {
         out_i[(int64_t)u * gstride] = kInf;
       }
     }
     return;
   }
-  double* od = FINAL ? out_d + (int64_t)(n - 1) * gstride : nullptr;
+  double* od = FINAL ? out_d : nullptr;
   int32_t* oi = FINAL ? nullptr : out_i + (int64_t)(n - 1) * gstride;
   for (int u = n - 1; u >= 0; --u) {
     while (tp != kNoSite && tt > u) {
@@ -462,7 +482,7 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
       // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360); after resetBuffer old is 10000 everywhere,
       // so the read of the old value is skipped
       *od = fmin(edt_distance(res, val), fresh ? 10000.0 : *od);
-      od -= gstride;
+      od -= BRICK ? ((u & 7) ? (int64_t)32 : ojump) : gstride;
     } else {
       *oi = val;
       oi -= gstride;
@@ -488,27 +508,51 @@ k_edt_x(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, int n
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t plane = (int64_t)ny * nz;
   if (r >= plane) return;
-  envelope_row<MAXN, true>(in + r, plane, nx, nullptr, dist + r, res, fresh);
+  envelope_row<MAXN, true>(in + r, plane, nx, nullptr, dist + r + (int64_t)(nx - 1) * plane, res, fresh);
+}
+
+// pass x into a field kept in 8 x 8 x 4 bricks (DistLayout).  A warp takes 4 y x 8 z rows: its loads of the linear int32
+// input are four full 32-byte sectors per x, its stores two full 128-byte lines of the bricks (4 y x 4 z each).
+template <int MAXN>
+__global__ void __launch_bounds__(128)
+k_edt_x_brick(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, DistLayout lay, double res, bool fresh) {
+  const int lane = threadIdx.x & 31;
+  const int nz8 = (lay.nz + 7) >> 3;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // warp -> (group of 4 y, block of 8 z)
+  const int y = (int)(w / nz8) * 4 + (lane >> 3), z = (int)(w % nz8) * 8 + (lane & 7);
+  if (y >= lay.ny || z >= lay.nz) return;
+  const int64_t plane = (int64_t)lay.ny * lay.nz;
+  envelope_row<MAXN, true, true>(in + (int64_t)y * lay.nz + z, plane, nx, nullptr, dist + lay.at(nx - 1, y, z), res, fresh,
+                                 ((int64_t)lay.nby * lay.nbz << 8) - 7 * 32);
 }
 
 template <int MAXN>
 static cudaError_t launch_yx(const int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
-                             bool fresh, cudaStream_t st, cudaEvent_t ev_mid) {
+                             bool fresh, cudaStream_t st, cudaEvent_t ev_mid, const DistLayout* lay) {
   const int threads = 128;
   {
     const int64_t rows = (int64_t)nx * nz;
     k_edt_y<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d1, d2, nx, ny, nz);
   }
   if (ev_mid) cudaEventRecord(ev_mid, st);
-  {
+  if (lay && lay->bricks) {
+    const int64_t warps = (int64_t)((ny + 3) / 4) * ((nz + 7) / 8);
+    k_edt_x_brick<MAXN><<<(unsigned)((warps + 3) / 4), threads, 0, st>>>(d2, dist, nx, *lay, res, fresh);
+  } else {
     const int64_t rows = (int64_t)ny * nz;
     k_edt_x<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d2, dist, nx, ny, nz, res, fresh);
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_fill(double* dist, uint8_t* occ, int64_t n, double dval, cudaStream_t st) {
-  k_fill<<<148 * 8, 256, 0, st>>>(dist, occ, n, dval);
+cudaError_t launch_fill(double* dist, int64_t ndist, uint8_t* occ, int64_t n, double dval, cudaStream_t st) {
+  k_fill<<<148 * 8, 256, 0, st>>>(dist, ndist, occ, n, dval);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_relayout(const double* src, double* dst, const DistLayout& lay, int nx, bool to_linear, cudaStream_t st) {
+  const int64_t n = (int64_t)nx * lay.ny * lay.nz;
+  k_relayout<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, lay, nx, to_linear);
   return cudaGetLastError();
 }
 
@@ -529,9 +573,9 @@ cudaError_t launch_build_quads_box(const SdfView& S, const double* dist, void* q
   return cudaGetLastError();
 }
 
-cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, int ny, int nz, double dval, cudaStream_t st) {
+cudaError_t launch_box_reset(double* dist, uint8_t* occ, const VoxelBox& b, const DistLayout& lay, double dval, cudaStream_t st) {
   const int64_t n = (int64_t)b.wx * b.wy * b.wz;
-  k_box_reset<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dist, occ, b, ny, nz, dval, n);
+  k_box_reset<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dist, occ, b, lay, dval, n);
   return cudaGetLastError();
 }
 
@@ -549,9 +593,10 @@ cudaError_t launch_set_boxes(int nx, int ny, int nz, uint8_t* occ, const int32_t
   return cudaGetLastError();
 }
 
-// full EDT: occ -> d1 (z) -> d2 (y) -> dist (x).  ev[0..3] (nullable) bracket the three passes.
+// full EDT: occ -> d1 (z) -> d2 (y) -> dist (x).  ev[0..3] (nullable) bracket the three passes.  lay: layout of `dist`
+// (nullptr = linear)
 cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
-                       bool fresh, cudaStream_t st, cudaEvent_t* ev) {
+                       bool fresh, cudaStream_t st, cudaEvent_t* ev, const DistLayout* lay) {
   const int64_t ncols = (int64_t)nx * ny;
   if (ev) cudaEventRecord(ev[0], st);
   {
@@ -570,15 +615,15 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
   const int maxn = nx > ny ? nx : ny;
   cudaError_t e;
   if (maxn <= 256)
-    e = launch_yx<256>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
+    e = launch_yx<256>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr, lay);
   else if (maxn <= 1024)
-    e = launch_yx<1024>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
+    e = launch_yx<1024>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr, lay);
   else if (maxn <= 2048)
-    e = launch_yx<2048>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
+    e = launch_yx<2048>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr, lay);
   else if (maxn <= 4096)
-    e = launch_yx<4096>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
+    e = launch_yx<4096>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr, lay);
   else if (maxn <= 16384)
-    e = launch_yx<16384>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr);
+    e = launch_yx<16384>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr, lay);
   else
     return cudaErrorInvalidValue;
   if (ev) cudaEventRecord(ev[3], st);
@@ -592,13 +637,14 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
 // k_box_merge folds min(new, old) back — identical to the reference's arithmetic because the squared distances are
 // exact integers whatever the coordinate origin of the rows.
 cudaError_t launch_edt_window(const uint8_t* occ, uint8_t* wocc, int32_t* d1, int32_t* d2, double* wdist, double* dist,
-                              const VoxelBox& b, int ny, int nz, double res, cudaStream_t st, cudaEvent_t* ev) {
+                              const VoxelBox& b, const DistLayout& lay, double res, cudaStream_t st, cudaEvent_t* ev) {
+  const int ny = lay.ny, nz = lay.nz;
   const int64_t n = (int64_t)b.wx * b.wy * b.wz;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   k_box_gather_occ<<<blocks, 256, 0, st>>>(occ, wocc, b, ny, nz, n);
-  cudaError_t e = launch_edt(wocc, d1, d2, wdist, b.wx, b.wy, b.wz, res, true, st, ev);
+  cudaError_t e = launch_edt(wocc, d1, d2, wdist, b.wx, b.wy, b.wz, res, true, st, ev, nullptr);  // compact grid: linear
   if (e != cudaSuccess) return e;
-  k_box_merge<<<blocks, 256, 0, st>>>(wdist, dist, b, ny, nz, n);
+  k_box_merge<<<blocks, 256, 0, st>>>(wdist, dist, b, lay, n);
   if (ev) cudaEventRecord(ev[3], st);  // the merge belongs to the x pass
   return cudaGetLastError();
 }
@@ -627,12 +673,12 @@ __global__ void k_query(SdfView S, const double* __restrict__ pos, int64_t n, do
   const int x0 = max(min(ix, S.nx - 1), 0), x1 = max(min(ix + 1, S.nx - 1), 0);
   const int y0 = max(min(iy, S.ny - 1), 0), y1 = max(min(iy + 1, S.ny - 1), 0);
   const int z0 = max(min(iz, S.nz - 1), 0), z1 = max(min(iz + 1, S.nz - 1), 0);
-  const int64_t sx = (int64_t)S.ny * S.nz, sy = S.nz;
   const double* D = S.dist;
-  const double v000 = D[x0 * sx + y0 * sy + z0], v001 = D[x0 * sx + y0 * sy + z1];
-  const double v010 = D[x0 * sx + y1 * sy + z0], v011 = D[x0 * sx + y1 * sy + z1];
-  const double v100 = D[x1 * sx + y0 * sy + z0], v101 = D[x1 * sx + y0 * sy + z1];
-  const double v110 = D[x1 * sx + y1 * sy + z0], v111 = D[x1 * sx + y1 * sy + z1];
+  const DistLayout& L = S.lay;
+  const double v000 = D[L.at(x0, y0, z0)], v001 = D[L.at(x0, y0, z1)];
+  const double v010 = D[L.at(x0, y1, z0)], v011 = D[L.at(x0, y1, z1)];
+  const double v100 = D[L.at(x1, y0, z0)], v101 = D[L.at(x1, y0, z1)];
+  const double v110 = D[L.at(x1, y1, z0)], v111 = D[L.at(x1, y1, z1)];
   // unfused, reference order: results are bit-identical to the CPU path
   const double ex = __dsub_rn(1.0, dx), ey = __dsub_rn(1.0, dy), ez = __dsub_rn(1.0, dz);
   const double v00 = __dadd_rn(__dmul_rn(ex, v000), __dmul_rn(dx, v100));
@@ -691,7 +737,7 @@ __global__ void k_query_dynamic(SdfView S, const double* __restrict__ boxes, int
     if (!in_map(x, y, z)) return -1.0;
     const int vx = (int)floor(__dmul_rn(__dsub_rn(x, S.ox), S.res_inv)), vy = (int)floor(__dmul_rn(__dsub_rn(y, S.oy), S.res_inv)),
               vz = (int)floor(__dmul_rn(__dsub_rn(z, S.oz), S.res_inv));
-    return S.dist[((int64_t)vx * S.ny + vy) * S.nz + vz];
+    return S.dist[S.lay.at(vx, vy, vz)];
   };
   const double px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
   if (coarse) {  // evaluateCoarseEDT (:124-137)

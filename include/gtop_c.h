@@ -116,14 +116,16 @@ int gtop_sdf_last_edt_ms(const gtop_sdf* sdf, float ms[4]);
  * the gather copy (0 for maps that keep none), ms[5] = start of the update to evaluator-ready */
 int gtop_sdf_last_update_ms(const gtop_sdf* sdf, float ms[6]);
 /* how the evaluation kernels read the field: has_quad_copy = 1 -> from the xy-quad copy (4x the field, two 256-bit loads
- * per sample; maps whose copy stays under GTOP_QUAD_LIMIT_MB, default 1024), 0 -> straight from the distance field (big
- * maps: eight 64-bit loads per sample, no copy to keep or rebuild).  resident_bytes = device memory the map holds. */
+ * per sample; maps whose copy stays under GTOP_QUAD_LIMIT_MB, default 1024), 0 -> straight from the distance field, which
+ * such maps keep in 8 x 8 x 4 voxel bricks instead of the reference's linear order (big maps: eight 64-bit loads per
+ * sample, no copy to keep or rebuild; up / download convert).  resident_bytes = device memory the map holds. */
 int gtop_sdf_gather_layout(const gtop_sdf* sdf, int32_t* has_quad_copy, int64_t* resident_bytes);
 int gtop_sdf_download_distance(const gtop_sdf* sdf, double* host);
 int gtop_sdf_upload_distance(gtop_sdf* sdf, const double* host);
 int gtop_sdf_download_occupancy(const gtop_sdf* sdf, int32_t* host);
 int gtop_sdf_upload_occupancy(gtop_sdf* sdf, const int32_t* host);
-/* device pointer of the fp64 distance buffer (nx*ny*nz doubles), for callers that share it */
+/* device pointer of the fp64 distance buffer (nx*ny*nz doubles, x*ny*nz + y*nz + z), for callers that share it;
+ * GTOP_E_INVALID for a map without a quad copy (its field is bricked, see gtop_sdf_gather_layout) */
 int gtop_sdf_distance_device_ptr(const gtop_sdf* sdf, const double** dev_ptr);
 /* batched getDistWithGradTrilinear: host in/out; out-of-map -> dist=-1, grad=0; returns
  * the out-of-map count through *n_out_of_map (nullable) */

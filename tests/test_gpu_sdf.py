@@ -12,9 +12,20 @@ from oracle import OracleMap
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["quad", "bricks"])
+def field_layout(request, monkeypatch):
+    """Every map test runs on both layouts of the distance field: linear + xy-quad copy (maps under GTOP_QUAD_LIMIT_MB)
+    and 8 x 8 x 4 bricks without a copy (big maps; forced here with a limit of 0)."""
+    monkeypatch.setenv("GTOP_QUAD_LIMIT_MB", "1024" if request.param == "quad" else "0")
+    return request.param
+
+
 def _gpu_map(origin, res, size):
+    import os
     from grad_traj_optimization_b200.api import SdfMap
-    return SdfMap(origin, res, size)
+    gm = SdfMap(origin, res, size)
+    assert gm.gather_layout()[0] == (os.environ["GTOP_QUAD_LIMIT_MB"] != "0")
+    return gm
 
 
 def _both(origin, res, size, pts):

@@ -1,0 +1,139 @@
+// bigmap_gather_bench.cu — what bounds the trilinear corner gather on a field that is far bigger than L2 and the TLB
+// reach (BASELINE configs[3]: 2000 x 2000 x 400 fp64 = 12.8 GB), and what a tiled layout would buy.
+//
+// Access pattern of k_eval_traj_seg on that map: 4,096 trajectories x 10 segments x 30 samples; a quarter-warp owns
+// a segment and lane j of it takes samples j, j+8, ... (4 per lane); consecutive samples are ~3 voxels apart along a
+// random horizontal direction.  Per sample: the 8 corners of a cell = 4 (x,y) columns x 2 adjacent heights.
+//   L0  linear            [x][y][z]                       x-neighbour 6.4 MB away
+//   L1  xy tiles 16 x 16  [x/16][y/16][x%16][y%16][z]     x-neighbour 51 KB away inside a tile
+//   L2  xy tiles 8 x 8    [x/8][y/8][x%8][y%8][z]
+//   L3  bricks 4 x 4 x 4  [x/4][y/4][z/4][x%4][y%4][z%4]  all corners inside 512 B for 27/64 of the cells
+//   L4  linear with the x planes folded onto 64 (410 MB, ~200 pages of 2 MB): same sector pattern, few pages
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/bigmap_gather_bench tools/bigmap_gather_bench.cu
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+constexpr int NX = 2000, NY = 2000, NZ = 400;
+
+__device__ __forceinline__ unsigned hash(unsigned x) {
+  x ^= x >> 16, x *= 0x7feb352du, x ^= x >> 15, x *= 0x846ca68bu, x ^= x >> 16;
+  return x;
+}
+
+template <int L>
+__device__ __forceinline__ size_t vox(int x, int y, int z) {
+  if (L >= 1000) {  // bricks 2^a x 2^b x 2^c, L = 1000 + 100 a + 10 b + c: [x>>a][y>>b][z>>c][x&..][y&..][z&..]
+    constexpr int LL = L >= 1000 ? L - 1000 : 0;
+    constexpr int a = LL / 100, b = (LL / 10) % 10, c = LL % 10;
+    constexpr int nby = (NY + (1 << b) - 1) >> b, nbz = (NZ + (1 << c) - 1) >> c;
+    const size_t brick = ((size_t)(x >> a) * nby + (y >> b)) * nbz + (z >> c);
+    return (brick << (a + b + c)) + (((x & ((1 << a) - 1)) << (b + c)) | ((y & ((1 << b) - 1)) << c) | (z & ((1 << c) - 1)));
+  }
+  if (L == 0) return ((size_t)x * NY + y) * NZ + z;
+  if (L == 4) return ((size_t)(x & 63) * NY + y) * NZ + z;  // the x planes folded onto 64: 410 MB, ~200 pages
+  if (L == 1) return ((((size_t)(x >> 4) * (NY / 16) + (y >> 4)) << 8) + ((x & 15) << 4) + (y & 15)) * NZ + z;
+  if (L == 2) return ((((size_t)(x >> 3) * (NY / 8) + (y >> 3)) << 6) + ((x & 7) << 3) + (y & 7)) * NZ + z;
+  return ((((size_t)(x >> 2) * (NY / 4) + (y >> 2)) * (NZ / 4) + (z >> 2)) << 6) + ((x & 3) << 4) + ((y & 3) << 2) + (z & 3);
+}
+
+// one quarter-warp per (trajectory, segment); `spread` = side of the square region the trajectories start in
+template <int L>
+__global__ void __launch_bounds__(128) k_gather(const double* __restrict__ D, double* out, int nseg, int spread, float step) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int seg = gid >> 3, j = gid & 7;
+  if (seg >= nseg) return;
+  const unsigned traj = seg / 10, s = seg % 10;
+  const unsigned h = hash(traj * 977u + 12345u);
+  const float ang = (float)((h >> 18) & 1023) * (6.2831853f / 1024.f);
+  const float cx = __cosf(ang), cy = __sinf(ang);
+  // trajectory start inside the region, far enough from the border for 300 samples of `step` voxels
+  const float bx = 950.f + (float)(hash(h) % (unsigned)spread) - 0.5f * spread;
+  const float by = 950.f + (float)(hash(h + 1u) % (unsigned)spread) - 0.5f * spread;
+  const float bz = 100.f + (float)(h & 127);
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int smp = s * 30 + j + 8 * k;
+    if (j + 8 * k >= 30) break;
+    const float px = bx + smp * step * cx, py = by + smp * step * cy, pz = bz + smp * 0.05f;
+    int x0 = (int)px, y0 = (int)py, z0 = (int)pz;
+    x0 = max(0, min(x0, NX - 2)), y0 = max(0, min(y0, NY - 2)), z0 = max(0, min(z0, NZ - 2));
+    const double* r00 = D + vox<L>(x0, y0, z0);
+    const double* r01 = D + vox<L>(x0, y0 + 1, z0);
+    const double* r10 = D + vox<L>(x0 + 1, y0, z0);
+    const double* r11 = D + vox<L>(x0 + 1, y0 + 1, z0);
+    const int dz = (L == 3 || L >= 1000) ? (int)(vox<L>(x0, y0, z0 + 1) - vox<L>(x0, y0, z0)) : 1;
+    acc += (__ldg(r00) + __ldg(r00 + dz)) + (__ldg(r01) + __ldg(r01 + dz)) + (__ldg(r10) + __ldg(r10 + dz)) +
+           (__ldg(r11) + __ldg(r11 + dz));
+  }
+  if (acc == 1234.5) out[0] = acc;
+}
+
+static float g_warm;
+template <int L>
+static double run(const double* D, double* out, int spread, float step, char* flush, size_t flush_bytes) {
+  const int nseg = 4096 * 10;
+  const int grid = (nseg * 8 + 127) / 128;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  float best = 1e9f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaMemsetAsync(flush, rep, flush_bytes);  // L2 flush between repetitions
+    cudaEventRecord(e0);
+    k_gather<L><<<grid, 128>>>(D, out, nseg, spread, step);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  // steady state of an optimiser loop: the same samples again, nothing flushed in between
+  float warm = 1e9f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    k_gather<L><<<grid, 128>>>(D, out, nseg, spread, step);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < warm) warm = ms;
+  }
+  g_warm = warm;
+  return best;
+}
+
+int main() {
+  const size_t nvox = (size_t)NX * NY * NZ;
+  double* D;
+  if (cudaMalloc(&D, nvox * 8 + (1 << 20)) != cudaSuccess) return 2;
+  cudaMemset(D, 0, nvox * 8);
+  double* out;
+  cudaMalloc(&out, 64);
+  char* flush;
+  const size_t fb = 512u << 20;
+  cudaMalloc(&flush, fb);
+  printf("{");
+  bool first = true;
+  auto report = [&](const char* name, float st, double ms) {
+    printf("%s\"%s_step%.1f\": {\"us_cold\": %.1f, \"us_repeat\": %.1f}", first ? "" : ", ", name, st, ms * 1e3, g_warm * 1e3);
+    first = false;
+  };
+  const float steps[2] = {1.2f, 3.3f};
+  for (int si = 0; si < 2; ++si) {
+    const float st = steps[si];
+    report("linear", st, run<0>(D, out, 1000, st, flush, fb));
+    report("xy16", st, run<1>(D, out, 1000, st, flush, fb));
+    report("brick_4x4x4", st, run<1222>(D, out, 1000, st, flush, fb));
+    report("brick_4x4x8", st, run<1223>(D, out, 1000, st, flush, fb));
+    report("brick_8x8x4", st, run<1332>(D, out, 1000, st, flush, fb));
+    report("brick_8x8x8", st, run<1333>(D, out, 1000, st, flush, fb));
+    report("brick_2x2x16", st, run<1114>(D, out, 1000, st, flush, fb));
+    report("brick_4x4x16", st, run<1224>(D, out, 1000, st, flush, fb));
+    report("brick_16x16x4", st, run<1442>(D, out, 1000, st, flush, fb));
+    report("linear_x_folded_64", st, run<4>(D, out, 1000, st, flush, fb));
+  }
+  printf("}\n");
+  return cudaGetLastError() != cudaSuccess;
+}
