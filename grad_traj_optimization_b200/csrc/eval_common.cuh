@@ -166,12 +166,11 @@ __device__ __forceinline__ void sdf_gather(const SdfView& S, double px, double p
   const int z0 = max(min(iz, S.nz - 1), 0), z1 = max(min(iz + 1, S.nz - 1), 0);
   if (kPlain) {
     const int x1 = min(x0 + 1, S.nx - 1), y1 = min(y0 + 1, S.ny - 1);
-    // brick address = column part (x,y) + height part (z): [x>>3][y>>3][z>>2][x&7][y&7][z&3]
+    // brick address = column part (x,y) + height part (z), see DistLayout
     const int bx0 = (x0 >> 3) * S.lay.nby, bx1 = (x1 >> 3) * S.lay.nby;
-    const int ox0 = (x0 & 7) << 5, ox1 = (x1 & 7) << 5, oy0 = (y0 & 7) << 2, oy1 = (y1 & 7) << 2;
-    const size_t c00 = ((size_t)(bx0 + (y0 >> 3)) * S.lay.nbz << 8) + (ox0 | oy0), c01 = ((size_t)(bx0 + (y1 >> 3)) * S.lay.nbz << 8) + (ox0 | oy1);
-    const size_t c10 = ((size_t)(bx1 + (y0 >> 3)) * S.lay.nbz << 8) + (ox1 | oy0), c11 = ((size_t)(bx1 + (y1 >> 3)) * S.lay.nbz << 8) + (ox1 | oy1);
-    const int h0 = ((z0 >> 2) << 8) | (z0 & 3), h1 = ((z1 >> 2) << 8) | (z1 & 3);
+    const size_t c00 = ((size_t)(bx0 + (y0 >> 3)) * S.lay.nbz << 8) + DistLayout::col(x0, y0), c01 = ((size_t)(bx0 + (y1 >> 3)) * S.lay.nbz << 8) + DistLayout::col(x0, y1);
+    const size_t c10 = ((size_t)(bx1 + (y0 >> 3)) * S.lay.nbz << 8) + DistLayout::col(x1, y0), c11 = ((size_t)(bx1 + (y1 >> 3)) * S.lay.nbz << 8) + DistLayout::col(x1, y1);
+    const int h0 = ((z0 >> 2) << 8) | DistLayout::hgt(z0), h1 = ((z1 >> 2) << 8) | DistLayout::hgt(z1);
     const double* __restrict__ D = S.dist;
     c.q0.v00 = __ldg(D + c00 + h0), c.q0.v01 = __ldg(D + c01 + h0), c.q0.v10 = __ldg(D + c10 + h0), c.q0.v11 = __ldg(D + c11 + h0);
     c.q1.v00 = __ldg(D + c00 + h1), c.q1.v01 = __ldg(D + c01 + h1), c.q1.v10 = __ldg(D + c10 + h1), c.q1.v11 = __ldg(D + c11 + h1);

@@ -15,21 +15,26 @@ namespace gtop {
 // Where voxel (x,y,z) of the fp64 distance field lives.
 //   linear (bricks == 0): x*ny*nz + y*nz + z, as in the reference (sdf_map.cpp:92,97-98), z fastest — maps that also keep
 //                         the xy-quad copy below (the evaluation kernels then never read `dist`);
-//   bricks (bricks == 1): 8 x 8 x 4 (x,y,z) voxel bricks of 2 KB, [x>>3][y>>3][z>>2][x&7][y&7][z&3] — maps too big for a
-//                         quad copy, whose trilinear gathers go straight to the field in HBM.  In the linear order the
-//                         four (x,y) columns of a cell are 8*nz bytes and 8*ny*nz bytes (6.4 MB on the 2000x2000x400
-//                         map) apart: four 32-byte sectors from four DRAM pages per sample.  In a brick the 4 heights of a
-//                         column are one sector, a 128-byte line is 4 y x 4 z, and the x-neighbour is 256 bytes away:
-//                         consecutive samples of a trajectory (about a voxel apart) reuse the same lines.  Measured
-//                         (tools/bigmap_gather_bench.cu, 4,096 x 300 samples on 12.8 GB): 117 us linear, 59 us in
-//                         these bricks (44 us when the same samples are gathered again: the touched lines fit L2).
+//   bricks (bricks == 1): 8 x 8 x 4 (x,y,z) voxel bricks of 2 KB made of 2 x 2 x 2 voxel chunks of 64 bytes (what one L2
+//                         miss fetches from HBM): [x>>3][y>>3][z>>2] [x>>1&3][y>>1&3][z>>1&1] [x&1][y&1][z&1] — maps too
+//                         big for a quad copy, whose trilinear gathers go straight to the field in HBM.  In the linear
+//                         order the four (x,y) columns of a cell are 8*nz bytes and 8*ny*nz bytes (6.4 MB on the
+//                         2000x2000x400 map) apart: four sectors from four DRAM pages per sample.  Here a cell lies in
+//                         1-8 chunks of one or two neighbouring bricks (3.4 on average, 1 when it is aligned), and
+//                         consecutive samples of a trajectory (about a voxel apart) reuse them.  Measured
+//                         (tools/bigmap_gather_bench.cu, 4,096 x 300 samples on 12.8 GB): 117 us linear, 57 us for
+//                         bricks in plain [x&7][y&7][z&3] order, 49 us for this order (40 us when the same samples are
+//                         gathered again: the touched lines fit L2).
 // The occupancy and the EDT's int32 intermediates stay linear.
 struct DistLayout {
   int ny, nz;    // grid
   int nby, nbz;  // bricks along y and z (ceil(ny/8), ceil(nz/4))
   int bricks;
+  // offset of column (x,y) / of height z inside their brick (bit-disjoint)
+  GTOP_HD static int col(int x, int y) { return (((x >> 1) & 3) << 6) | (((y >> 1) & 3) << 4) | ((x & 1) << 2) | ((y & 1) << 1); }
+  GTOP_HD static int hgt(int z) { return (((z >> 1) & 1) << 3) | (z & 1); }
   GTOP_HD int64_t at(int x, int y, int z) const {
-    if (bricks) return ((((int64_t)(x >> 3) * nby + (y >> 3)) * nbz + (z >> 2)) << 8) + (((x & 7) << 5) | ((y & 7) << 2) | (z & 3));
+    if (bricks) return ((((int64_t)(x >> 3) * nby + (y >> 3)) * nbz + (z >> 2)) << 8) + (col(x, y) | hgt(z));
     return ((int64_t)x * ny + y) * nz + z;
   }
 };

@@ -393,7 +393,8 @@ cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev
 // Rows up to 8192 long keep every intermediate below 2^31 (u^2 + 3 n^2 <= 2.7e8), so the intersection
 // is a 32-bit division; longer rows use 64-bit arithmetic.
 // Output: out_i (int32, same stride as the input) or, FINAL, the fp64 distances: out_d points at the row's LAST element
-// and walks down by gstride (linear field) or, BRICK, by 32 doubles inside an 8-voxel x-brick and `ojump` across bricks.
+// and walks down by gstride (linear field) or, BRICK, through the bricks of DistLayout: from x to x - 1 the address drops
+// by 4 doubles inside a chunk (x odd), by 60 to the previous chunk of the brick, by `ojump` to the previous brick.
 template <int MAXN, bool FINAL, bool BRICK = false>
 __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int64_t gstride, int n,
                                              int32_t* __restrict__ out_i, double* __restrict__ out_d, double res,
@@ -461,7 +462,7 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
     for (int u = n - 1; u >= 0; --u) {
       if (FINAL) {
         if (fresh) *od = 10000.0;
-        od -= BRICK ? ((u & 7) ? (int64_t)32 : ojump) : gstride;
+        od -= BRICK ? ((u & 1) ? (int64_t)4 : ((u & 7) ? (int64_t)60 : ojump)) : gstride;
       } else {
         out_i[(int64_t)u * gstride] = kInf;
       }
@@ -482,7 +483,7 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
       // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360); after resetBuffer old is 10000 everywhere,
       // so the read of the old value is skipped
       *od = fmin(edt_distance(res, val), fresh ? 10000.0 : *od);
-      od -= BRICK ? ((u & 7) ? (int64_t)32 : ojump) : gstride;
+      od -= BRICK ? ((u & 1) ? (int64_t)4 : ((u & 7) ? (int64_t)60 : ojump)) : gstride;
     } else {
       *oi = val;
       oi -= gstride;
@@ -512,7 +513,8 @@ k_edt_x(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, int n
 }
 
 // pass x into a field kept in 8 x 8 x 4 bricks (DistLayout).  A warp takes 4 y x 8 z rows: its loads of the linear int32
-// input are four full 32-byte sectors per x, its stores two full 128-byte lines of the bricks (4 y x 4 z each).
+// input are four full 32-byte sectors per x, its stores eight full sectors (2 y x 2 z each) of two bricks; the other
+// half of their 64-byte chunks follows with the next x.
 template <int MAXN>
 __global__ void __launch_bounds__(128)
 k_edt_x_brick(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, DistLayout lay, double res, bool fresh) {
@@ -523,7 +525,7 @@ k_edt_x_brick(const int32_t* __restrict__ in, double* __restrict__ dist, int nx,
   if (y >= lay.ny || z >= lay.nz) return;
   const int64_t plane = (int64_t)lay.ny * lay.nz;
   envelope_row<MAXN, true, true>(in + (int64_t)y * lay.nz + z, plane, nx, nullptr, dist + lay.at(nx - 1, y, z), res, fresh,
-                                 ((int64_t)lay.nby * lay.nbz << 8) - 7 * 32);
+                                 ((int64_t)lay.nby * lay.nbz << 8) - (3 * 64 + 4));
 }
 
 template <int MAXN>

@@ -24,6 +24,13 @@ __device__ __forceinline__ unsigned hash(unsigned x) {
 
 template <int L>
 __device__ __forceinline__ size_t vox(int x, int y, int z) {
+  if (L == 2000 || L == 2001) {  // 8 x 8 x 4 bricks whose 64-byte chunks are 2 x 2 x 2 cells (2000) / lines are 2 x 2 x 4 (2001: [x/2][y/2][x&1][y&1][z&3])
+    constexpr int nby = (NY + 7) >> 3, nbz = (NZ + 3) >> 2;
+    const size_t brick = ((size_t)(x >> 3) * nby + (y >> 3)) * nbz + (z >> 2);
+    if (L == 2000)
+      return (brick << 8) + ((((x >> 1) & 3) << 6) | (((y >> 1) & 3) << 4) | (((z >> 1) & 1) << 3) | ((x & 1) << 2) | ((y & 1) << 1) | (z & 1));
+    return (brick << 8) + ((((x >> 1) & 3) << 6) | (((y >> 1) & 3) << 4) | ((x & 1) << 3) | ((y & 1) << 2) | (z & 3));
+  }
   if (L >= 1000) {  // bricks 2^a x 2^b x 2^c, L = 1000 + 100 a + 10 b + c: [x>>a][y>>b][z>>c][x&..][y&..][z&..]
     constexpr int LL = L >= 1000 ? L - 1000 : 0;
     constexpr int a = LL / 100, b = (LL / 10) % 10, c = LL % 10;
@@ -104,7 +111,13 @@ static double run(const double* D, double* out, int spread, float step, char* fl
   return best;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) {  // L2 fetch granularity hint (bytes): 32, 64 or 128
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[1]));
+  }
+  size_t gran = 0;
+  cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity);
+  fprintf(stderr, "L2 fetch granularity: %zu\n", gran);
   const size_t nvox = (size_t)NX * NY * NZ;
   double* D;
   if (cudaMalloc(&D, nvox * 8 + (1 << 20)) != cudaSuccess) return 2;
@@ -128,6 +141,8 @@ int main() {
     report("brick_4x4x4", st, run<1222>(D, out, 1000, st, flush, fb));
     report("brick_4x4x8", st, run<1223>(D, out, 1000, st, flush, fb));
     report("brick_8x8x4", st, run<1332>(D, out, 1000, st, flush, fb));
+    report("brick_8x8x4_chunk222", st, run<2000>(D, out, 1000, st, flush, fb));
+    report("brick_8x8x4_line224", st, run<2001>(D, out, 1000, st, flush, fb));
     report("brick_8x8x8", st, run<1333>(D, out, 1000, st, flush, fb));
     report("brick_2x2x16", st, run<1114>(D, out, 1000, st, flush, fb));
     report("brick_4x4x16", st, run<1224>(D, out, 1000, st, flush, fb));
