@@ -363,8 +363,11 @@ __device__ __forceinline__ double sqrt_small_int(int v) {
   return fma(fma(-t, t, a), h, t);
 }
 // res * sqrt(val) as the reference computes it (sdf_map.cpp:356-360), bit for bit
+// kLong: rows longer than 8192 voxels, whose squared distances may exceed kFastSqrtMax (a compile-time fact of the row
+// bucket: the test costs 3 instructions per voxel)
+template <bool kLong>
 __device__ __forceinline__ double edt_distance(double res, int val) {
-  if (val > kFastSqrtMax) return res * sqrt((double)val);  // (rows longer than 8192 voxels only)
+  if (kLong && val > kFastSqrtMax) return res * sqrt((double)val);
   const double r = sqrt_small_int(max(val, 1));            // occupied voxel: sqrt(0) = 0 without the seed's infinity
   return res * (val == 0 ? 0.0 : r);
 }
@@ -482,7 +485,7 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
     if (FINAL) {
       // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360); after resetBuffer old is 10000 everywhere,
       // so the read of the old value is skipped
-      *od = fmin(edt_distance(res, val), fresh ? 10000.0 : *od);
+      *od = fmin(edt_distance<(MAXN > 8192)>(res, val), fresh ? 10000.0 : *od);
       od -= BRICK ? ((u & 1) ? (int64_t)4 : ((u & 7) ? (int64_t)60 : ojump)) : gstride;
     } else {
       *oi = val;
@@ -614,7 +617,9 @@ cudaError_t launch_edt(const uint8_t* occ, int32_t* d1, int32_t* d2, double* dis
     // two-sweep kernel hits L1, and it measured faster than 8/16 ballot words in registers (4.05 vs 4.74 ms at nz=400)
   }
   if (ev) cudaEventRecord(ev[1], st);
-  const int maxn = nx > ny ? nx : ny;
+  // (columns taller than 8192 voxels can produce squared distances above kFastSqrtMax: they take the long-row bucket,
+  // the only one that keeps the range test of edt_distance)
+  const int maxn = nz > 8192 ? 16384 : (nx > ny ? nx : ny);
   cudaError_t e;
   if (maxn <= 256)
     e = launch_yx<256>(d1, d2, dist, nx, ny, nz, res, fresh, st, ev ? ev[2] : nullptr, lay);

@@ -85,7 +85,9 @@ def test_edt_random_small_grids_vs_bruteforce(gtop_lib, dims, nocc, seed):
     # BASELINE config 4), <= 4096, <= 16384 (64-bit intersection arithmetic above 8192), on both row axes
     ((2000, 8, 8), 40, 21, False), ((8, 2000, 8), 40, 22, False), ((4000, 4, 4), 30, 23, False), ((4, 4000, 4), 30, 24, False),
     ((9000, 2, 2), 25, 25, False), ((2, 9000, 2), 25, 26, False), ((2000, 8, 8), 40, 27, True), ((4, 4000, 4), 30, 28, True),
-    ((9000, 2, 2), 25, 29, True), ((2000, 3, 5), 1, 30, False), ((2000, 2, 2), 6000, 31, False)])
+    ((9000, 2, 2), 25, 29, True), ((2000, 3, 5), 1, 30, False), ((2000, 2, 2), 6000, 31, False),
+    # a column taller than 8192 voxels: squared distances beyond the fast integer square root's range
+    ((2, 3, 16000), 1, 32, False)])
 def test_edt_long_rows_vs_oracle_and_bruteforce(gtop_lib, dims, nocc, seed, windowed):
     """sdf_map.cpp:266-368 on grids whose x / y rows are as long as the large map's (and longer)."""
     res = 0.25  # (dims * res is exact in binary: ceil(size / res) gives back dims)
