@@ -401,7 +401,7 @@ cudaError_t launch_check_sqrt(long long vmax, unsigned long long* mismatches_dev
 template <int MAXN, bool FINAL, bool BRICK = false>
 __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int64_t gstride, int n,
                                              int32_t* __restrict__ out_i, double* __restrict__ out_d, double res,
-                                             bool fresh, int64_t ojump = 0) {
+                                             int fresh, int64_t ojump = 0) {
   typedef typename std::conditional<(MAXN <= 8192), int, long long>::type wide_t;
   // Hull sites as a linked list embedded in a per-site array: st[u] = (start_u | prev_u << 16, g(u)) is written when
   // site u is pushed — every lane of a warp is at the same u, so the store is coalesced (a compacted stack indexed by
@@ -474,24 +474,51 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
   }
   double* od = FINAL ? out_d : nullptr;
   int32_t* oi = FINAL ? nullptr : out_i + (int64_t)(n - 1) * gstride;
-  for (int u = n - 1; u >= 0; --u) {
-    while (tp != kNoSite && tt > u) {
-      ts = tp;
-      const int2 e = st[ts];
-      tt = e.x & 0xffff, tp = (unsigned)e.x >> 16, tg = e.y;
-    }
-    const int d = u - ts;
-    const int val = d * d + tg;
-    if (FINAL) {
-      // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360); after resetBuffer old is 10000 everywhere,
-      // so the read of the old value is skipped
-      *od = fmin(edt_distance<(MAXN > 8192)>(res, val), fresh ? 10000.0 : *od);
-      od -= BRICK ? ((u & 1) ? (int64_t)4 : ((u & 7) ? (int64_t)60 : ojump)) : gstride;
+  // min(resolution*sqrt(val), old)  (sdf_map.cpp:356-360).  `fresh` (warp-uniform) picks one of three copies of the
+  // loop: 0 = read the old value; 1 = the buffer holds 10000 everywhere (just reset): no read; 2 = as 1, and no distance
+  // of this grid can reach 10000: plain store (the min is 3 of ~110 instructions per voxel)
+  auto fill = [&](auto mode_tag) {
+    constexpr int kMode = decltype(mode_tag)::value;
+    auto emit = [&](int u) {  // voxel u of the row: pop down to its site, evaluate, store (the caller moves od / oi)
+      while (tp != kNoSite && tt > u) {
+        ts = tp;
+        const int2 e = st[ts];
+        tt = e.x & 0xffff, tp = (unsigned)e.x >> 16, tg = e.y;
+      }
+      const int d = u - ts;
+      const int val = d * d + tg;
+      if (FINAL) {
+        const double dnew = edt_distance<(MAXN > 8192)>(res, val);
+        *od = kMode == 2 ? dnew : fmin(dnew, kMode == 1 ? 10000.0 : *od);
+      } else {
+        *oi = val;
+      }
+    };
+    int u = n - 1;
+    if (FINAL && BRICK) {
+      // pairs (odd x, even x) share a 64-byte chunk: the step inside a pair is a constant, one select per pair
+      if (!(u & 1)) {
+        emit(u);
+        od -= (u & 7) ? (int64_t)60 : ojump;
+        --u;
+      }
+      for (; u >= 1; u -= 2) {
+        emit(u);
+        od -= 4;
+        emit(u - 1);
+        od -= ((u - 1) & 7) ? (int64_t)60 : ojump;
+      }
     } else {
-      *oi = val;
-      oi -= gstride;
+      for (; u >= 0; --u) {
+        emit(u);
+        if (FINAL) od -= gstride;
+        else oi -= gstride;
+      }
     }
-  }
+  };
+  if (FINAL && fresh == 2) fill(std::integral_constant<int, 2>{});
+  else if (FINAL && fresh == 1) fill(std::integral_constant<int, 1>{});
+  else fill(std::integral_constant<int, 0>{});
 }
 
 // pass y: row = (x,z); element y at ((x*ny + y)*nz + z)
@@ -502,13 +529,13 @@ k_edt_y(const int32_t* __restrict__ in, int32_t* __restrict__ out, int nx, int n
   if (r >= (int64_t)nx * nz) return;
   const int x = (int)(r / nz), z = (int)(r % nz);
   const int64_t base = (int64_t)x * ny * nz + z;
-  envelope_row<MAXN, false>(in + base, nz, ny, out + base, nullptr, 0.0, false);
+  envelope_row<MAXN, false>(in + base, nz, ny, out + base, nullptr, 0.0, 0);
 }
 
 // pass x: row = (y,z); element x at (x*ny*nz + (y*nz + z)); writes the fp64 distance buffer
 template <int MAXN>
 __global__ void __launch_bounds__(128)
-k_edt_x(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, int ny, int nz, double res, bool fresh) {
+k_edt_x(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, int ny, int nz, double res, int fresh) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t plane = (int64_t)ny * nz;
   if (r >= plane) return;
@@ -520,7 +547,7 @@ k_edt_x(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, int n
 // half of their 64-byte chunks follows with the next x.
 template <int MAXN>
 __global__ void __launch_bounds__(128)
-k_edt_x_brick(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, DistLayout lay, double res, bool fresh) {
+k_edt_x_brick(const int32_t* __restrict__ in, double* __restrict__ dist, int nx, DistLayout lay, double res, int fresh) {
   const int lane = threadIdx.x & 31;
   const int nz8 = (lay.nz + 7) >> 3;
   const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // warp -> (group of 4 y, block of 8 z)
@@ -535,6 +562,10 @@ template <int MAXN>
 static cudaError_t launch_yx(const int32_t* d1, int32_t* d2, double* dist, int nx, int ny, int nz, double res,
                              bool fresh, cudaStream_t st, cudaEvent_t ev_mid, const DistLayout* lay) {
   const int threads = 128;
+  // fill mode of the x pass (envelope_row): after a reset nothing has to be read, and if no distance of this grid can
+  // reach the 10000 cap the min goes as well
+  const double dmax = res * sqrt((double)nx * nx + (double)ny * ny + (double)nz * nz);
+  const int mode = fresh ? (dmax * 1.000001 < 10000.0 ? 2 : 1) : 0;
   {
     const int64_t rows = (int64_t)nx * nz;
     k_edt_y<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d1, d2, nx, ny, nz);
@@ -542,10 +573,10 @@ static cudaError_t launch_yx(const int32_t* d1, int32_t* d2, double* dist, int n
   if (ev_mid) cudaEventRecord(ev_mid, st);
   if (lay && lay->bricks) {
     const int64_t warps = (int64_t)((ny + 3) / 4) * ((nz + 7) / 8);
-    k_edt_x_brick<MAXN><<<(unsigned)((warps + 3) / 4), threads, 0, st>>>(d2, dist, nx, *lay, res, fresh);
+    k_edt_x_brick<MAXN><<<(unsigned)((warps + 3) / 4), threads, 0, st>>>(d2, dist, nx, *lay, res, mode);
   } else {
     const int64_t rows = (int64_t)ny * nz;
-    k_edt_x<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d2, dist, nx, ny, nz, res, fresh);
+    k_edt_x<MAXN><<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(d2, dist, nx, ny, nz, res, mode);
   }
   return cudaGetLastError();
 }

@@ -120,6 +120,22 @@ def test_edt_empty_map_is_10000_everywhere(gtop_lib):
     assert np.all(gm.distance() == 10000.0)  # sdf_map.cpp:22,358-360
 
 
+def test_edt_distances_capped_by_the_reset_value(gtop_lib):
+    """min(resolution*sqrt(val), old) with old = 10000 after resetBuffer (sdf_map.cpp:22, :358-360): on a grid coarse enough
+    for distances beyond 10000 the far voxels keep the reset value (the x pass only drops the min when no distance of the
+    grid can reach it)."""
+    origin, res, size = [0.0, 0.0, 0.0], 1500.0, [9 * 1500.0, 7 * 1500.0, 5 * 1500.0]
+    occ = np.zeros((9, 7, 5), dtype=np.int32)
+    occ[0, 0, 0] = 1
+    om = OracleMap(origin, res, size)
+    gm = _gpu_map(origin, res, size)
+    om.set_occupancy_buffer(occ), gm.upload_occupancy(occ)
+    om.update_esdf(), gm.update_esdf()
+    d = gm.distance()
+    assert np.array_equal(d, om.distance())
+    assert d.max() == 10000.0 and (d == 10000.0).sum() > 10 and d.reshape(9, 7, 5)[0, 0, 0] == 0.0
+
+
 def test_edt_update_twice_and_reset(gtop_lib):
     """updateESDF3d takes min(new, old) (:358-360): a second obstacle set can only lower distances
     until resetBuffer is called."""
