@@ -452,7 +452,9 @@ __device__ __forceinline__ void envelope_row(const int32_t* __restrict__ g, int6
         // Sep(i,u) = floor((u^2 - i^2 + g(u) - g(i)) / (2(u-i))): last x where site i still wins
         // (num >= 0: the pops above leave a top with F(tt, ts) <= F(tt, u), i.e. num >= 2 tt (u - ts))
         const wide_t num = (wide_t)u * u - (wide_t)ts * ts + (wide_t)gu - (wide_t)tg;
-        const int w = 1 + ((MAXN <= 8192) ? floor_div_pos((int)num, 2 * (u - ts)) : (int)(num / (wide_t)(2 * (u - ts))));
+        // (neighbouring sites are the common case on dense rows: a shift instead of the division sequence)
+        const int w = 1 + ((u - ts == 1) ? (int)(num >> 1)
+                                         : ((MAXN <= 8192) ? floor_div_pos((int)num, 2 * (u - ts)) : (int)(num / (wide_t)(2 * (u - ts)))));
         if (w < n) {
           tp = ts, ts = u, tt = w, tg = gu;
           st[u] = make_int2(tt | (tp << 16), tg);
