@@ -253,9 +253,9 @@ k_edt_z_reg(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t 
 
 // pass z, vectorised: 4 voxels per lane (one 32-bit occupancy load, one 128-bit store), 128 per warp step, for
 // columns with nz % 4 == 0 and nz <= 128*NCH.  The nearest occupied voxel below / above comes from a per-lane scan of
-// its 4 voxels plus a warp max- / min-scan of the lanes' last / first occupied index (shuffles), instead of one ballot
-// round per 32 voxels: ~0.6 warp instructions per voxel instead of 2.2 (the ballot kernel is issue-bound: 79 % issue
-// utilisation at 24 % of DRAM bandwidth on the 2000x2000x400 map).
+// its 4 voxels plus, for the other lanes, a bit scan of the ballot of occupied lanes and one shuffle of that lane's last /
+// first occupied index, instead of one ballot round per 32 voxels: well under one warp instruction per voxel instead of
+// 2.2 (the ballot kernel is issue-bound: 79 % issue utilisation at 24 % of DRAM bandwidth on the 2000x2000x400 map).
 template <int NCH>
 __global__ void __launch_bounds__(256)
 k_edt_z_vec(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t ncols, int nz) {
@@ -272,6 +272,11 @@ k_edt_z_vec(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t 
       const int z0 = c * 128 + lane * 4;
       w[c] = z0 < nz ? o[z0 >> 2] : 0u;
     }
+    // lanes that hold an occupied voxel, per chunk: the nearest occupied voxel in ANOTHER lane is then one bit scan of
+    // this mask plus one shuffle (a 5-step shuffle scan per sweep was a quarter of the kernel's instructions)
+    unsigned m[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) m[c] = __ballot_sync(0xffffffffu, w[c] != 0u);
     // backward sweep: index of the nearest occupied voxel at or above each voxel (kNone if none)
     int up[NCH][4];
     int carry = kNone;
@@ -283,22 +288,16 @@ k_edt_z_vec(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t 
 #pragma unroll
       for (int j = 3; j >= 0; --j)
         if ((w[c] >> (8 * j)) & 0xffu) first = z0 + j;
-      // exclusive min-scan over the HIGHER lanes
-      int sc = first;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_down_sync(0xffffffffu, sc, off);
-        if (lane + off < 32) sc = min(sc, t);
-      }
-      int above = __shfl_down_sync(0xffffffffu, sc, 1);
-      above = (lane == 31) ? carry : min(above, carry);
-      int cur = above;
+      const unsigned higher = m[c] & (0xfffffffeu << lane);  // occupied lanes above this one
+      const int v = __shfl_sync(0xffffffffu, first, higher ? __ffs(higher) - 1 : lane);
+      int cur = higher ? v : carry;
 #pragma unroll
       for (int j = 3; j >= 0; --j) {
         if ((w[c] >> (8 * j)) & 0xffu) cur = z0 + j;
         up[c][j] = cur;
       }
-      carry = min(carry, __shfl_sync(0xffffffffu, sc, 0));
+      const int lowest = __shfl_sync(0xffffffffu, first, m[c] ? __ffs(m[c]) - 1 : 0);
+      carry = m[c] ? lowest : carry;
     }
     // forward sweep: nearest occupied at or below, combine, square, store
     carry = -kNone;
@@ -309,15 +308,9 @@ k_edt_z_vec(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t 
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if ((w[c] >> (8 * j)) & 0xffu) last = z0 + j;
-      int sc = last;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, sc, off);
-        if (lane >= off) sc = max(sc, t);
-      }
-      int below = __shfl_up_sync(0xffffffffu, sc, 1);
-      below = (lane == 0) ? carry : max(below, carry);
-      int cur = below;
+      const unsigned lower = m[c] & ((1u << lane) - 1u);  // occupied lanes below this one
+      const int v = __shfl_sync(0xffffffffu, last, lower ? 31 - __clz(lower) : lane);
+      int cur = lower ? v : carry;
       int r[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -327,7 +320,8 @@ k_edt_z_vec(const uint8_t* __restrict__ occ, int32_t* __restrict__ out, int64_t 
         r[j] = best >= (kNone >> 1) ? kInf : best * best;
       }
       if (z0 < nz) d[z0 >> 2] = make_int4(r[0], r[1], r[2], r[3]);
-      carry = max(carry, __shfl_sync(0xffffffffu, sc, 31));
+      const int highest = __shfl_sync(0xffffffffu, last, m[c] ? 31 - __clz(m[c]) : 0);
+      carry = m[c] ? highest : carry;
     }
   }
 }
