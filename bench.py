@@ -199,7 +199,7 @@ def edt_record(gm, fill, reps, peak, name):
     bytes_total = nv * (25 + (40 if quad else 0))
     return {"map": name, "grid": list(gm.grid), "voxels": nv, "ms_z": best[0], "ms_y": best[1], "ms_x": best[2],
             "ms_edt": best[3], "ms_gather_copy": best[4], "ms_update_to_evaluator_ready": best[5],
-            "gather_layout": "xy-quad copy" if quad else "distance field (no copy)", "resident_bytes": resident,
+            "gather_layout": "xy-quad copy" if quad else "distance field in 8x8x4 bricks (no copy)", "resident_bytes": resident,
             "edt_roofline": {"bound": "hbm", "achieved": nv * 25 / (best[3] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": nv * 25 / (best[3] * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_voxel": 25},
             "ready_GBps_incl_gather_copy": bytes_total / (best[5] * 1e-3) / 1e9}
@@ -216,7 +216,7 @@ def other_shapes(torch, api, fx, gm, peak, steps):
     wps = np.stack([fx.random_waypoints(p, m, dist, fx.MAP_A["map_origin"], fx.MAP_A["resolution"]) for p in range(B)])
     ps = api.ProblemSet.from_paths(wps, api.make_params(fx.PARAMS_OPTI), setup="device")
     ms, _ = DeviceTimer(torch, api, gm, ps, ps.x0(), 1).run(max(steps, 50), 5)
-    out.append(shape_record("configs[1]: 1,024 distinct 7-waypoint problems on Map A (k_eval_traj)", ms, B, m, 30, ps.n, peak))
+    out.append(shape_record("configs[1]: 1,024 distinct 7-waypoint problems on Map A (k_eval_traj_seg)", ms, B, m, 30, ps.n, peak))
     del ps
     # configs[4]: m = 30, 200 samples per segment, 16 waypoint sets x 1,024 starts
     m, ns, sets = 30, 200, 16
@@ -241,7 +241,7 @@ def other_shapes(torch, api, fx, gm, peak, steps):
     t = DeviceTimer(torch, api, gb, ps, ps.x0(), 1)
     ms, _ = t.run(max(steps, 50), 5)
     c = t.Cd[0].cpu().numpy()
-    out.append(shape_record("configs[3]: 4,096 distinct 11-waypoint problems on Map B, 12.8 GB field in HBM (k_eval_traj)",
+    out.append(shape_record("configs[3]: 4,096 distinct 11-waypoint problems on Map B, 12.8 GB field in HBM in 8x8x4 bricks (k_eval_traj_seg; every step evaluates the same samples, as an optimiser loop does)",
                             ms, B, m, 30, ps.n, peak, {"finite": bool(np.isfinite(c).all()), "out_of_map_samples": ps.take_out_of_map()}))
     del t, ps, gb
     torch.cuda.empty_cache()
