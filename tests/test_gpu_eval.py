@@ -407,3 +407,47 @@ def test_segment_parallel_general_kernel_is_bit_identical(gtop_lib, vel_acc):
         rows = np.nonzero(pid == p)[0][:4]
         cr, gr, _, _ = opt.eval_batch(X[rows], 2)
         assert rel_cost_err(c[rows], cr).max() <= TOL and rel_grad_err(g[rows], gr).max() <= TOL
+
+
+def test_big_field_in_hbm_parity(gtop_lib):
+    """A map whose field does not fit L2 and whose quad copy would exceed the 1 GiB limit (726 x 718 x 162 voxels = 676 MB:
+    the BASELINE configs[3] situation at a size the oracle builds in seconds): the field lives in 8 x 8 x 4 bricks, none of
+    the grid dimensions is a multiple of the brick.  GPU EDT bit-exact against the oracle, then distinct problems
+    (k_eval_traj_seg) and a multi-start batch (k_eval_mma), both gathering straight from HBM, against the oracle."""
+    from oracle import OracleMap
+    api = _api()
+    res, dims = 0.0625, (726, 718, 162)
+    size = np.array(dims, dtype=np.float64) * res
+    origin = np.array([-0.5 * size[0], -0.5 * size[1], 0.0])
+    gm = api.SdfMap(origin, res, size)
+    assert gm.grid == dims and not gm.gather_layout()[0]
+    boxes = fx.box_pillars(350, 9, dims, half_width_vox=5, height_vox=(40, 150), margin_vox=40)
+    gm.set_occupancy_boxes(boxes), gm.update_esdf()
+    occ = np.zeros(dims, dtype=np.int32)
+    for b in boxes:
+        occ[b[0]:b[3] + 1, b[1]:b[4] + 1, b[2]:b[5] + 1] = 1
+    om = OracleMap(origin, res, size)
+    assert om.grid == dims
+    om.set_occupancy_buffer(occ), om.update_esdf()
+    assert np.array_equal(gm.distance(), om.distance())
+    # distinct problems, one start each
+    m, B = 10, 384
+    free = fx.boxes_clearance_fn(boxes, origin, res, 0.5)
+    wps = np.stack([fx.random_waypoints_free(p, m, free, 19.0, -18.0 + 34.0 * ((p * 0.6180339887) % 1.0), start_y_span=16.0)
+                    for p in range(B)])
+    ps = api.ProblemSet.from_paths(wps, api.make_params(fx.PARAMS_OPTI), setup="device")
+    x0, (lb, ub) = ps.x0(), ps.bounds()
+    X = np.clip(x0 + np.random.default_rng(3).normal(0.0, 0.25, x0.shape), lb, ub)
+    c, g, oob = ps.eval_host(gm, X, step=2, starts_per_problem=1)
+    assert oob == 0
+    for p in range(0, B, 7):
+        cr, gr, _, _ = oracle_problem(fx.PARAMS_OPTI, om, wps[p]).eval_batch(X[p:p + 1], 2)
+        assert rel_cost_err(c[p:p + 1], cr).max() <= TOL and rel_grad_err(g[p:p + 1], gr).max() <= TOL
+    # multi-start batch of two of the problems
+    ps2 = api.ProblemSet.from_paths(wps[:2], api.make_params(fx.PARAMS_OPTI))
+    Xm = np.concatenate([fx.multi_starts(x0[p], lb[p], ub[p], 256, seed=11 + p) for p in range(2)])
+    cm, gm_, _ = ps2.eval_host(gm, Xm, step=2, starts_per_problem=256)
+    for p in range(2):
+        sl = slice(256 * p, 256 * (p + 1))
+        cr, gr, _, _ = oracle_problem(fx.PARAMS_OPTI, om, wps[p]).eval_batch(Xm[sl], 2)
+        assert rel_cost_err(cm[sl], cr).max() <= TOL and rel_grad_err(gm_[sl], gr).max() <= TOL
