@@ -113,6 +113,19 @@ def test_edt_long_rows_vs_oracle_and_bruteforce(gtop_lib, dims, nocc, seed, wind
     assert np.array_equal(d_gpu, om.brute_edt())
 
 
+def test_distance_device_pointer_only_for_the_linear_layout(gtop_lib, field_layout):
+    """gtop_sdf_distance_device_ptr hands out the buffer in the reference's index order; a bricked field refuses (its
+    callers would read the wrong voxels) and points at the download."""
+    import ctypes as C
+    gm = _gpu_map([0, 0, 0], 0.5, [8, 6, 4])
+    p = C.c_void_p()
+    rc = gtop_lib.gtop_sdf_distance_device_ptr(gm.h, C.byref(p))
+    if field_layout == "quad":
+        assert rc == 0 and p.value
+    else:
+        assert rc != 0 and b"bricks" in gtop_lib.gtop_last_error()
+
+
 def test_edt_empty_map_is_10000_everywhere(gtop_lib):
     gm = _gpu_map([0, 0, 0], 0.5, [8, 6, 4])
     gm.reset()
