@@ -496,6 +496,11 @@ static bool force_general() {
   return v;
 }
 
+// would launch_eval take the multi-start kernel (whose x / gradient blocks move by bulk copies)?
+bool eval_takes_mma_kernel(const ProbLayout& PL, const EvalScalars& E, int64_t B, int num_problems, int64_t starts_per_problem) {
+  return !force_general() && !E.vel_acc && eval_mma_applicable(PL, B, num_problems, starts_per_problem);
+}
+
 cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* prob, int num_problems,
                         const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
                         int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,

@@ -23,6 +23,7 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
                         const EvalScalars& E, const double* X, int64_t B, int64_t traj_offset,
                         int64_t starts_per_problem, double* cost, double* grad, unsigned long long* oob_counter,
                         int max_ctas, cudaStream_t stream);
+bool eval_takes_mma_kernel(const ProbLayout& PL, const EvalScalars& E, int64_t B, int num_problems, int64_t starts_per_problem);
 cudaError_t launch_fill(double* dist, int64_t ndist, uint8_t* occ, int64_t n, double dval, cudaStream_t st);
 cudaError_t launch_relayout(const double* src, double* dst, const DistLayout& lay, int nx, bool to_linear, cudaStream_t st);
 cudaError_t launch_build_quads(const SdfView& S, const double* dist, void* quad, cudaStream_t st);
@@ -1008,6 +1009,45 @@ int gtop_eval_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, const do
   gtop_problems* pr = const_cast<gtop_problems*>(cpr);  // staging buffers are a cache
   CU(cudaSetDevice(pr->device));
   const int n = pr->layout.n;
+  const EvalScalars E = make_scalars(pr->prm, step);
+  // Pinned (or registered) host buffers are addressable from the device: the multi-start kernel then reads its x blocks
+  // and writes its gradient blocks straight across PCIe with the bulk copies it uses anyway (5 KB per group of 8
+  // trajectories, hundreds of groups in flight) — one launch, both directions busy from the first block to the last, no
+  // staging copies and no cross-stream hand-offs (each costs ~10 us on the chunked pipeline below): 1.14 against 1.29 ms
+  // per 65,536 batch.  Pageable buffers, and batches for the general kernels (8-byte loads), take the staged pipeline.
+  static const bool zero_copy = [] { const char* e = std::getenv("GTOP_HOST_ZEROCOPY"); return !e || std::atoi(e) != 0; }();
+  if (zero_copy && eval_takes_mma_kernel(pr->layout, E, B, pr->np, starts)) {
+    auto device_view = [](const void* h) -> void* {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, h) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+    };
+    const double* zx = static_cast<const double*>(device_view(X));
+    double* zc = static_cast<double*>(device_view(cost));
+    double* zg = static_cast<double*>(device_view(grad));
+    if (zx && zc && zg) {
+      // (measured and dropped: the tail of the batch brought in by DMA meanwhile and evaluated by a second launch — the
+      // link, not the initiator, is the limit: 1.20-1.33 ms against 1.14; x by DMA in chunks with direct stores: 1.21-1.49)
+      cudaStream_t s_k = pr->streams[0];
+      cudaError_t err = launch_eval(sdf->view, pr->layout, pr->rec, pr->np, E, zx, B, off, starts, zc, zg, pr->oob, 0, s_k);
+      ++g_launches;
+      if (err == cudaSuccess && n_oob && pr->h_oob) {
+        err = cudaMemcpyAsync(pr->h_oob, pr->oob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_k);
+        if (err == cudaSuccess) err = cudaMemsetAsync(pr->oob, 0, sizeof(unsigned long long), s_k);
+      }
+      const cudaError_t es = cudaStreamSynchronize(s_k);
+      if (err == cudaSuccess) err = es;
+      CU(err);
+      if (n_oob) {
+        if (!pr->h_oob) return gtop_problems_take_out_of_map(pr, n_oob);
+        *n_oob = (int64_t)*pr->h_oob;
+      }
+      return GTOP_OK;
+    }
+  }
   if (pr->cap < B) {
     cudaFree(pr->dX), cudaFree(pr->dcost), cudaFree(pr->dgrad);
     pr->dX = pr->dcost = pr->dgrad = nullptr, pr->cap = 0;
@@ -1017,7 +1057,6 @@ int gtop_eval_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, const do
     if (e != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("eval staging: ") + cudaGetErrorString(e));
     pr->cap = B;
   }
-  const EvalScalars E = make_scalars(pr->prm, step);
   // chunked pipeline over three streams: all H2D copies of x back to back on the copy-in stream, the kernels
   // on the compute stream as their chunk lands, cost/gradient copied out on the copy-out stream as each
   // kernel finishes (the two PCIe directions and the SMs are busy at the same time)

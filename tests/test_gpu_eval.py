@@ -451,3 +451,32 @@ def test_big_field_in_hbm_parity(gtop_lib):
         sl = slice(256 * p, 256 * (p + 1))
         cr, gr, _, _ = oracle_problem(fx.PARAMS_OPTI, om, wps[p]).eval_batch(Xm[sl], 2)
         assert rel_cost_err(cm[sl], cr).max() <= TOL and rel_grad_err(gm_[sl], gr).max() <= TOL
+
+
+def test_pinned_host_buffers_are_evaluated_in_place(gtop_lib, monkeypatch):
+    """gtop_eval_batch_host on pinned buffers lets the multi-start kernel read x and write cost / gradient across PCIe
+    directly (no staging copies); pageable buffers and GTOP_HOST_ZEROCOPY=0 take the chunked staging pipeline: same bits,
+    same out-of-map count, ragged offsets included."""
+    import torch
+    api = _api()
+    cfg = fx.load_cfg("opti_node")
+    om = oracle_map_from_cfg(cfg)
+    gm = _gpu_map_from_oracle(om)
+    opt = oracle_problem(cfg, om, cfg["waypoints"])
+    X = _starts(opt, 4096, seed=5)
+    X[7, 2 * opt.num_dp:2 * opt.num_dp + 9:3] += 4.0   # above the ceiling: out-of-map samples
+    ps = api.ProblemSet.from_paths(cfg["waypoints"], api.make_params(cfg["params"]))
+    c0, g0, o0 = ps.eval_host(gm, X, step=2, starts_per_problem=4096)          # pageable numpy buffers
+    assert o0 > 0
+    Xh = torch.from_numpy(X).pin_memory()
+    Gh, Ch = torch.empty(X.shape, dtype=torch.float64).pin_memory(), torch.empty((X.shape[0],), dtype=torch.float64).pin_memory()
+    n0 = gtop_lib.gtop_kernel_launch_count()
+    _, _, o1 = ps.eval_host(gm, Xh, step=2, starts_per_problem=4096, cost=Ch, grad=Gh)
+    assert gtop_lib.gtop_kernel_launch_count() - n0 == 1                       # one launch, no chunks
+    assert o1 == o0 and np.array_equal(Ch.numpy(), c0) and np.array_equal(Gh.numpy(), g0)
+    Gh.zero_(), Ch.zero_()
+    _, _, o2 = ps.eval_host(gm, Xh[1000:3001], step=2, starts_per_problem=4096, traj_offset=1000, cost=Ch[1000:3001], grad=Gh[1000:3001])
+    assert np.array_equal(Ch.numpy()[1000:3001], c0[1000:3001]) and np.array_equal(Gh.numpy()[1000:3001], g0[1000:3001])
+    assert not Ch.numpy()[:1000].any() and not Gh.numpy()[3001:].any()
+    c_ref, g_ref, _, _ = opt.eval_batch(X[:64], 2)
+    assert rel_cost_err(c0[:64], c_ref).max() <= TOL and rel_grad_err(g0[:64], g_ref).max() <= TOL
