@@ -343,8 +343,12 @@ def run_ours(args):
             s1.record(timer.stream)
             barrier()
             solve_ms = s0.elapsed_time(s1)
+            Xs, Ms = Xh.clone().pin_memory(), Ch.clone().pin_memory()  # pinned: x in, x + min f out, solved in place
+            ps.solve_host(gm, Xs, step=2, maxeval=2, traj_offset=traj_offset, starts_per_problem=starts, minf=Ms)  # warm-up
+            Xs.copy_(Xh)
+            barrier()
             t0 = time.perf_counter()
-            ps.solve_host(gm, X, step=2, maxeval=100, traj_offset=traj_offset, starts_per_problem=starts)
+            ps.solve_host(gm, Xs, step=2, maxeval=100, traj_offset=traj_offset, starts_per_problem=starts, minf=Ms)
             solve_host_ms = (time.perf_counter() - t0) * 1e3
             solve_ms, solve_host_ms = max_over_ranks(solve_ms, solve_host_ms)
             solve = {"maxeval": 100, "ms": solve_ms, "solves_per_s": B * n_gpus / solve_ms * 1e3,

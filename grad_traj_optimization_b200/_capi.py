@@ -111,7 +111,7 @@ def lib():
         "gtop_objective": (C.c_double, [C.c_uint, dp, dp, vp]),
         "gtop_mma_minimize": (C.c_int, [C.c_uint, vp, vp, dp, dp, dp, dp, C.c_int, C.POINTER(C.c_int)]),
         "gtop_solve_batch_device": (C.c_int, [vp, vp, vp, i64, i64, i64, C.c_int, C.c_int, vp, vp]),
-        "gtop_solve_batch_host": (C.c_int, [vp, vp, dp, i64, i64, i64, C.c_int, C.c_int, dp]),
+        "gtop_solve_batch_host": (C.c_int, [vp, vp, vp, i64, i64, i64, C.c_int, C.c_int, vp]),
         "gtop_debug_check_sqrt": (C.c_int, [i64, C.POINTER(i64)]),
         "gtop_measure_fp64_peak": (C.c_int, [C.c_int, dp, dp]),
     }

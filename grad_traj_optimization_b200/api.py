@@ -323,8 +323,13 @@ class ProblemSet:
                                            int(step), cost.data_ptr(), grad.data_ptr(), stream))
 
 
-    def solve_host(self, sdf, X, step=OPT_SECOND_STEP, maxeval=100, traj_offset=0, starts_per_problem=1):
-        """Batched lock-step MMA (the optimiser loop of optimizeTrajectory) on the GPU: returns (best X, min f)."""
+    def solve_host(self, sdf, X, step=OPT_SECOND_STEP, maxeval=100, traj_offset=0, starts_per_problem=1, minf=None):
+        """Batched lock-step MMA (the optimiser loop of optimizeTrajectory) on the GPU: returns (best X, min f).
+        A numpy X is copied; a (pinned) torch CPU tensor is solved IN PLACE and `minf` must be a torch CPU tensor too."""
+        if hasattr(X, "data_ptr"):
+            check(lib().gtop_solve_batch_host(sdf.h, self.h, X.data_ptr(), X.shape[0], int(traj_offset), int(starts_per_problem),
+                                              int(step), int(maxeval), minf.data_ptr()))
+            return X, minf
         X = np.array(X, dtype=np.float64, order="C").reshape(-1, self.n)
         minf = np.empty(X.shape[0])
         check(lib().gtop_solve_batch_host(sdf.h, self.h, _dp(X), X.shape[0], int(traj_offset), int(starts_per_problem),

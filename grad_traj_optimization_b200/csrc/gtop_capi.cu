@@ -1194,16 +1194,26 @@ int gtop_solve_batch_host(const gtop_sdf* sdf, const gtop_problems* cpr, double*
   gtop_problems* pr = const_cast<gtop_problems*>(cpr);
   CU(cudaSetDevice(pr->device));
   const int n = pr->layout.n;
-  double *dX = nullptr, *dmin = nullptr;
-  cudaError_t e = cudaMalloc(&dX, sizeof(double) * B * n);
-  if (e == cudaSuccess) e = cudaMalloc(&dmin, sizeof(double) * B);
-  if (e == cudaSuccess) e = cudaMemcpy(dX, X, sizeof(double) * B * n, cudaMemcpyHostToDevice);
+  // x lives on the device for the whole loop: it goes in and comes back once, through the staging buffers the handle keeps
+  // for the *_host entry points (pinned host buffers copy at the link's rate; nothing is allocated per call)
+  if (pr->cap < B) {
+    cudaFree(pr->dX), cudaFree(pr->dcost), cudaFree(pr->dgrad);
+    pr->dX = pr->dcost = pr->dgrad = nullptr, pr->cap = 0;
+    cudaError_t ea = cudaMalloc(&pr->dX, sizeof(double) * B * n);
+    if (ea == cudaSuccess) ea = cudaMalloc(&pr->dgrad, sizeof(double) * B * n);
+    if (ea == cudaSuccess) ea = cudaMalloc(&pr->dcost, sizeof(double) * B);
+    if (ea != cudaSuccess) return fail(GTOP_E_ALLOC, std::string("solve staging: ") + cudaGetErrorString(ea));
+    pr->cap = B;
+  }
+  double *dX = pr->dX, *dmin = pr->dcost;
+  cudaStream_t st = pr->streams[0];
+  cudaError_t e = cudaMemcpyAsync(dX, X, sizeof(double) * B * n, cudaMemcpyHostToDevice, st);
   int rc = GTOP_OK;
-  if (e == cudaSuccess) rc = gtop_solve_batch_device(sdf, cpr, dX, B, off, starts, step, maxeval, dmin, pr->streams[0]);
-  if (e == cudaSuccess && rc == GTOP_OK) e = cudaStreamSynchronize(pr->streams[0]);
-  if (e == cudaSuccess && rc == GTOP_OK) e = cudaMemcpy(X, dX, sizeof(double) * B * n, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && rc == GTOP_OK && minf) e = cudaMemcpy(minf, dmin, sizeof(double) * B, cudaMemcpyDeviceToHost);
-  cudaFree(dX), cudaFree(dmin);
+  if (e == cudaSuccess) rc = gtop_solve_batch_device(sdf, cpr, dX, B, off, starts, step, maxeval, dmin, st);
+  if (e == cudaSuccess && rc == GTOP_OK) e = cudaMemcpyAsync(X, dX, sizeof(double) * B * n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == GTOP_OK && minf) e = cudaMemcpyAsync(minf, dmin, sizeof(double) * B, cudaMemcpyDeviceToHost, st);
+  const cudaError_t es = cudaStreamSynchronize(st);  // whatever happened, nothing still writes into the caller's buffers
+  if (e == cudaSuccess) e = es;
   if (rc != GTOP_OK) return rc;
   CU(e);
   return GTOP_OK;

@@ -142,4 +142,10 @@ def test_batched_on_device_mma_matches_the_cpu_solves(gtop_lib, name, starts):
     gold = np.load(os.path.join(ROOT, "tests", "golden", "fixtures_solve.npz"))
     dev_g = np.linalg.norm(sample_traj(gold["%s_coeff_maxeval100" % name], T) - sample_traj(ps.coeff_from_x(X[0]), T), axis=1).max()
     assert dev_g <= 1e-4
+    # pinned torch tensors are solved in place (x in, x + min f out): the same loop, the same bits
+    import torch
+    Xp = torch.from_numpy(np.ascontiguousarray(X0)).pin_memory()
+    Mp = torch.empty((starts,), dtype=torch.float64).pin_memory()
+    ps.solve_host(gm, Xp, step=2, maxeval=100, starts_per_problem=starts, minf=Mp)
+    assert np.array_equal(Xp.numpy(), X) and np.array_equal(Mp.numpy(), minf)
     print("batched MMA vs CPU solves: worst trajectory deviation %.3e m over %d starts" % (worst, starts))
