@@ -241,6 +241,8 @@ k_eval_traj(SdfView S, ProbLayout PL, const double* __restrict__ prob, int num_p
   // 2^(j/16) table for exp2_tab: the only block-level synchronisation of the kernel
   double* xtab = smem + wpc * kTrajPerWarp * traj_smem_doubles(m);
   exp2_tab_init(xtab, threadIdx.x, blockDim.x);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // programmatic dependent launch, see k_eval_traj_seg
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
 
   const int64_t b_raw = ((int64_t)blockIdx.x * wpc + warp) * kTrajPerWarp + q;
@@ -369,6 +371,10 @@ k_eval_traj_seg(SdfView S, ProbLayout PL, const double* __restrict__ prob, int n
 
   // ---- 1. boundary derivatives of the four trajectories in waypoint order ------------------------------------
   exp2_tab_init(xtab, tid, nthr);
+  // programmatic dependent launch: the next kernel of the stream may take free SM slots now; X and the problem records
+  // may come from the preceding kernel and are only read after the wait (worth ~2 us of a 15 us launch)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int i = tid; i < 4 * n; i += nthr) {
     const int qq = i / n, k = i - qq * n, a = k / P, jj = k - a * P;
     Wd_all[qq * 3 * nrow + a * nrow + 3 + jj] = X[traj_of(qq) * n + k];
@@ -496,6 +502,24 @@ static bool force_general() {
   return v;
 }
 
+// launch with programmatic stream serialization (the kernels above call griddepcontrol.wait before their first read of
+// anything a preceding kernel may have written); GTOP_PDL=0 turns it off
+template <class Kern, class... Args>
+static cudaError_t launch_pdl(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
+  static const bool pdl = [] { const char* e = std::getenv("GTOP_PDL"); return !e || std::atoi(e) != 0; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // would launch_eval take the multi-start kernel (whose x / gradient blocks move by bulk copies)?
 bool eval_takes_mma_kernel(const ProbLayout& PL, const EvalScalars& E, int64_t B, int num_problems, int64_t starts_per_problem) {
   return !force_general() && !E.vel_acc && eval_mma_applicable(PL, B, num_problems, starts_per_problem);
@@ -524,9 +548,8 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
       }
-      kern<<<(unsigned)ctas, W * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset, starts_per_problem,
-                                                     cost, grad, oob_counter);
-      return cudaGetLastError();
+      return launch_pdl(kern, (unsigned)ctas, W * 32, smem, stream, S, PL, prob, num_problems, E, X, B, traj_offset,
+                        starts_per_problem, cost, grad, oob_counter);
     }
   }
   // warps per CTA: as many as keep the CTA's shared memory modest (4 CTAs/SM at 16 warps/SM)
@@ -543,9 +566,8 @@ cudaError_t launch_eval(const SdfView& S, const ProbLayout& PL, const double* pr
   }
   const int64_t per_cta = (int64_t)wpc * kTrajPerWarp;
   const int64_t grid = (B + per_cta - 1) / per_cta;
-  kern<<<(unsigned)grid, wpc * 32, smem, stream>>>(S, PL, prob, num_problems, E, X, B, traj_offset, starts_per_problem,
-                                                   cost, grad, oob_counter);
-  return cudaGetLastError();
+  return launch_pdl(kern, (unsigned)grid, wpc * 32, smem, stream, S, PL, prob, num_problems, E, X, B, traj_offset,
+                    starts_per_problem, cost, grad, oob_counter);
 }
 
 }  // namespace gtop
