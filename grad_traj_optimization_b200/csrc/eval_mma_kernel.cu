@@ -150,14 +150,15 @@ struct Wp {
 // derivatives first, except for the last segment whose end derivatives live in columns 3..5 of d) with unfused
 // mul/add — the same 6-term sum as `L * d` (:273).  Lane j < 3 takes the power pair (2j, 2j+1) of all three axes: its six
 // Linv pairs are loaded once, and the four lanes of a trajectory read the same waypoint values (broadcast).
+// Lpre: the lane's six Linv pairs if the caller has loaded them already (under the copy of x), else nullptr
 template <bool kLast>
 __device__ __forceinline__ void pair_coef_phase(const Wp wp0, const Wp wp1, const double2* __restrict__ LiTP,
-                                                double2* __restrict__ coef, int j) {
+                                                double2* __restrict__ coef, int j, const double2* Lpre = nullptr) {
   if (j >= 3) return;
   const int p = j;
   double2 L[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r) L[r] = ldg_tab(LiTP + p * 6 + r);
+  for (int r = 0; r < 6; ++r) L[r] = Lpre ? Lpre[r] : ldg_tab(LiTP + p * 6 + r);
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const double *ws = wp0.p + a * wp0.s, *we = wp1.p + a * wp1.s;  // (p,v,a) of the segment's start / end waypoint
@@ -268,6 +269,25 @@ k_eval_mma(SdfView S, ProbLayout PL, PairSmem sm, const double* __restrict__ pro
     if (tid < 18) xin[8 * n + tid] = pr[PL.off_Df + tid];
     __syncthreads();
   }
+  // One pair per warp: what the pair reads from the problem record before its first sample — the sample counts and the
+  // Linv pairs of its two segments — is requested NOW, under the copy of x.  Taken one after the other behind x these were
+  // two more L2 round trips in the life of a CTA, and a small launch is made of those: one CTA per SM with ONE sample
+  // iteration per pair took 7.7 us (tools/kbench.py --ns 2; 7.3 with this), and the full batch gains 0.7 % (0.3317 ->
+  // 0.3294 ms).  Hoisting the first time record as well made the prologue shorter still and the sample loop slower
+  // (a different schedule); an L1 prefetch of the first records and of the epilogue's band rows changed nothing.
+  double2 preLa[6], preLb[6];
+  int pre_nsa = 0, pre_nsb = 0;
+  if (kOneRound && !E.skip_collision) {
+    const int sa = 2 * warp, sb = sa + 1;
+    pre_nsa = (int)pr[PL.off_ns + sa];
+    pre_nsb = sb < m ? (int)pr[PL.off_ns + sb] : 0;
+    if (j < 3) {
+      const double2* La = reinterpret_cast<const double2*>(pr + PL.off_LiTP + sa * 36) + j * 6;
+      const double2* Lb = reinterpret_cast<const double2*>(pr + PL.off_LiTP + (sb < m ? sb : sa) * 36) + j * 6;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) preLa[r] = ldg_tab(La + r), preLb[r] = ldg_tab(Lb + r);
+    }
+  }
   if (whole) mbar_wait(mbar, 0u);
 
   const double kA = -E.alpha * E.alpha_over_r * S.res_inv;  // gd*cd = -(alpha^2/r) e^2; grad scale 1/res
@@ -298,13 +318,13 @@ k_eval_mma(SdfView S, ProbLayout PL, PairSmem sm, const double* __restrict__ pro
       if (!E.skip_collision) {
         {
           const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + sa * 36);
-          if (sa == m - 1) pair_coef_phase<true>(wp0, wp1, LiTP, coef, j);
-          else pair_coef_phase<false>(wp0, wp1, LiTP, coef, j);
+          if (sa == m - 1) pair_coef_phase<true>(wp0, wp1, LiTP, coef, j, kOneRound ? preLa : nullptr);
+          else pair_coef_phase<false>(wp0, wp1, LiTP, coef, j, kOneRound ? preLa : nullptr);
         }
         if (hasb) {
           const double2* LiTP = reinterpret_cast<const double2*>(pr + PL.off_LiTP + sb * 36);
-          if (sb == m - 1) pair_coef_phase<true>(wp1, wp2, LiTP, coefB, j);
-          else pair_coef_phase<false>(wp1, wp2, LiTP, coefB, j);
+          if (sb == m - 1) pair_coef_phase<true>(wp1, wp2, LiTP, coefB, j, kOneRound ? preLb : nullptr);
+          else pair_coef_phase<false>(wp1, wp2, LiTP, coefB, j, kOneRound ? preLb : nullptr);
         }
         __syncwarp();
 
@@ -330,7 +350,7 @@ k_eval_mma(SdfView S, ProbLayout PL, PairSmem sm, const double* __restrict__ pro
           if (lane == 0) st_release_cta(fl + p, 1u);
         };
 
-        const int nsa = (int)pr[PL.off_ns + sa], nsb = hasb ? (int)pr[PL.off_ns + sb] : 0;
+        const int nsa = kOneRound ? pre_nsa : (int)pr[PL.off_ns + sa], nsb = kOneRound ? pre_nsb : (hasb ? (int)pr[PL.off_ns + sb] : 0);
         const int nit = (nsa + nsb + 3) >> 2;
         const bool mixed = nsb > 0 && (nsa & 3) != 0;  // one iteration holds samples of both segments
         // this lane samples the second segment from iteration ubl on (the mixed iteration splits the lanes)
